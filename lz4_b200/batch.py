@@ -1,0 +1,90 @@
+"""Batched block codec on device-resident torch tensors (the measured path).
+
+torch is plumbing here: it owns the device memory and the stream; all work is done by
+LZ4B200_* in liblz4_b200.so on raw pointers.
+"""
+import torch
+
+from . import _lib
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("device tensors required (got a CPU tensor)")
+
+
+def compress_bound(n):
+    return int(_lib.load().LZ4_compressBound(int(n)))
+
+
+def decompress_blocks(comp, offsets, sizes, block_capacity, out=None, out_stride=None, out_sizes=None,
+                      workspace=None, stream=None):
+    """Decode len(sizes) independent blocks.
+
+    comp: u8[*] device buffer; block i = comp[offsets[i] : offsets[i]+sizes[i]] (int64 / int32 device
+    tensors).  Block i is written to out[i*out_stride : ...] with capacity block_capacity.
+    Returns (out, out_sizes) -- out_sizes[i] is LZ4_decompress_safe's return value.
+    """
+    lib = _lib.load()
+    _need_cuda(comp, offsets, sizes, out)
+    n = int(sizes.numel())
+    stride = int(out_stride if out_stride is not None else block_capacity)
+    if out is None:
+        out = torch.empty(n * stride, dtype=torch.uint8, device=comp.device)
+    if out_sizes is None:
+        out_sizes = torch.empty(n, dtype=torch.int32, device=comp.device)
+    ws_bytes = int(lib.LZ4B200_decompress_workspace_bytes(n))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=comp.device)
+    assert offsets.dtype == torch.int64 and sizes.dtype == torch.int32 and comp.dtype == torch.uint8
+    rc = lib.LZ4B200_decompress_blocks(comp.data_ptr(), offsets.data_ptr(), sizes.data_ptr(), out.data_ptr(), None,
+                                       stride, None, int(block_capacity), out_sizes.data_ptr(), n,
+                                       workspace.data_ptr(), workspace.numel(), _stream_ptr(stream))
+    _lib.check(rc, "LZ4B200_decompress_blocks")
+    return out, out_sizes
+
+
+def compress_blocks(src, block_size, acceleration=1, slots=None, slot_stride=None, slot_capacity=None,
+                    out_sizes=None, src_sizes=None, stream=None):
+    """Compress src (u8 device tensor) as ceil(len/block_size) independent blocks.
+
+    Returns (slots, out_sizes): block i's bytes are slots[i*slot_stride : i*slot_stride+out_sizes[i]].
+    """
+    lib = _lib.load()
+    _need_cuda(src, slots)
+    total = int(src.numel())
+    n = (total + block_size - 1) // block_size if total else 0
+    cap = int(slot_capacity if slot_capacity is not None else compress_bound(block_size))
+    stride = int(slot_stride if slot_stride is not None else ((cap + 15) // 16) * 16)
+    if slots is None:
+        slots = torch.empty(max(n, 1) * stride, dtype=torch.uint8, device=src.device)
+    if out_sizes is None:
+        out_sizes = torch.empty(max(n, 1), dtype=torch.int32, device=src.device)
+    if src_sizes is None and n and total != n * block_size:
+        src_sizes = torch.full((n,), block_size, dtype=torch.int32, device=src.device)
+        src_sizes[-1] = total - (n - 1) * block_size
+    rc = lib.LZ4B200_compress_blocks(src.data_ptr(), int(block_size), src_sizes.data_ptr() if src_sizes is not None else None,
+                                     int(block_size), slots.data_ptr(), stride, cap, int(acceleration),
+                                     out_sizes.data_ptr(), n, _stream_ptr(stream))
+    _lib.check(rc, "LZ4B200_compress_blocks")
+    return slots, out_sizes[:n], stride
+
+
+def pack_blocks(slots, slot_stride, sizes, header_bytes=0, packed=None, stream=None):
+    """Gather variable-size blocks into one contiguous stream.  Returns (packed, offsets[n+1])."""
+    lib = _lib.load()
+    _need_cuda(slots, sizes)
+    n = int(sizes.numel())
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=slots.device)
+    if packed is None:
+        packed = torch.empty(n * (int(slot_stride) + header_bytes) + 16, dtype=torch.uint8, device=slots.device)
+    rc = lib.LZ4B200_pack_blocks(slots.data_ptr(), int(slot_stride), sizes.data_ptr(), n, packed.data_ptr(),
+                                 offsets.data_ptr(), int(header_bytes), _stream_ptr(stream))
+    _lib.check(rc, "LZ4B200_pack_blocks")
+    return packed, offsets

@@ -1,0 +1,64 @@
+"""Build liblz4_b200.so in-tree: nvcc (sm_100a) for the kernels, gcc for the C host layer.
+
+    python -m lz4_b200.build            # rebuild if sources are newer than the library
+    python -m lz4_b200.build --force
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "liblz4_b200.so")
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
+
+SOURCES = ["lz4_kernels.cu", "lz4_api.c"]
+HEADERS = [os.path.join(CSRC, "lz4_kernels.h"), os.path.join(ROOT, "include", "lz4_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math"]
+CC_FLAGS = ["-O2", "-fPIC", "-std=c99", "-Wall", "-Wextra", "-fvisibility=hidden",
+            "-I" + os.path.join(CUDA_HOME, "include")]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return r.stdout + r.stderr
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    if not os.path.exists(NVCC):
+        raise RuntimeError("nvcc not found at %s" % NVCC)
+    gcc = shutil.which("gcc") or "gcc"
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    ko = os.path.join(objdir, "lz4_kernels.o")
+    ao = os.path.join(objdir, "lz4_api.o")
+    log = _run([NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+               ["-c", os.path.join(CSRC, "lz4_kernels.cu"), "-o", ko])
+    log += _run([gcc] + CC_FLAGS + ["-c", os.path.join(CSRC, "lz4_api.c"), "-o", ao])
+    log += _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, ko, ao,
+                 "-Xlinker", "-Bsymbolic", "-lpthread"])
+    if verbose:
+        print(log)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built", LIB)

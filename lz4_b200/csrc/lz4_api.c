@@ -1,0 +1,382 @@
+/*
+ * lz4_api.c -- host side of liblz4_b200.so, in C (as the reference's lib/lz4.c is).
+ *
+ * Implements include/lz4_b200.h: the drop-in one-shot block API of lib/lz4.h over host pointers,
+ * the batched device-pointer API, and the host-buffer batch calls.  Every codec call runs the
+ * CUDA kernels of lz4_kernels.cu through the extern "C" launchers of lz4_kernels.h; there is no
+ * CPU implementation of the codec in this library.
+ */
+#include "../../include/lz4_b200.h"
+#include "lz4_kernels.h"
+
+#include <cuda_runtime_api.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------ */
+/* trivial host-only entry points (lz4.c:749-752)                                              */
+/* ------------------------------------------------------------------------------------------ */
+int LZ4_versionNumber(void) { return LZ4B200_VERSION_NUMBER; }
+const char* LZ4_versionString(void) { return "1.10.0"; }
+int LZ4_sizeofState(void) { return LZ4B200_STATE_BYTES; }
+int LZ4_compressBound(int inputSize)
+{
+    if ((unsigned)inputSize > (unsigned)LZ4B200_MAX_INPUT_SIZE) return 0;
+    return inputSize + inputSize / 255 + 16;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* CUDA context shared by the host-pointer calls                                               */
+/* ------------------------------------------------------------------------------------------ */
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static char g_cuda_error[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* where)
+{
+    snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s", where, cudaGetErrorString(e));
+    return LZ4B200_ERR_CUDA;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = cuda_fail(e_, #call); goto done; } } while (0)
+
+const char* LZ4B200_last_cuda_error(void) { return g_cuda_error; }
+uint64_t LZ4B200_launch_count(void) { return lz4k_launch_count(); }
+int LZ4B200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+#define N_PIPE 3   /* chunks in flight for the host-buffer batch calls */
+
+typedef struct {
+    int ready;
+    cudaStream_t stream[N_PIPE];
+    /* growable device buffers, one set per pipeline slot */
+    void* d_in[N_PIPE];   size_t in_cap[N_PIPE];
+    void* d_out[N_PIPE];  size_t out_cap[N_PIPE];
+    void* d_meta[N_PIPE]; size_t meta_cap[N_PIPE];
+    void* d_ws[N_PIPE];   size_t ws_cap[N_PIPE];
+} host_ctx;
+
+static host_ctx g_ctx;
+
+static int ctx_init(void)
+{
+    int rc = LZ4B200_OK, i;
+    if (g_ctx.ready) return LZ4B200_OK;
+    if (LZ4B200_device_count() <= 0) {
+        snprintf(g_cuda_error, sizeof(g_cuda_error), "no CUDA device: liblz4_b200 has no CPU fallback");
+        return LZ4B200_ERR_CUDA;
+    }
+    for (i = 0; i < N_PIPE; i++) CU(cudaStreamCreateWithFlags(&g_ctx.stream[i], cudaStreamNonBlocking));
+    g_ctx.ready = 1;
+done:
+    return rc;
+}
+
+static int grow(void** p, size_t* cap, size_t need)
+{
+    int rc = LZ4B200_OK;
+    if (need <= *cap) return rc;
+    if (*p) { CU(cudaFree(*p)); *p = NULL; *cap = 0; }
+    need = (need + (size_t)(1 << 20)) & ~(size_t)((1 << 20) - 1);
+    CU(cudaMalloc(p, need));
+    *cap = need;
+done:
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* batch layer: device pointers                                                                */
+/* ------------------------------------------------------------------------------------------ */
+size_t LZ4B200_decompress_workspace_bytes(int64_t nBlocks) { return lz4k_decode_workspace_bytes(nBlocks); }
+
+int LZ4B200_decompress_blocks(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
+                              void* d_dst, const int64_t* d_dstOff, int64_t dstStride,
+                              const int32_t* d_dstCap, int32_t dstCap,
+                              int32_t* d_outSize, int64_t nBlocks,
+                              void* d_workspace, size_t workspaceBytes, void* stream)
+{
+    lz4k_decode_args a;
+    cudaError_t e;
+    if (nBlocks < 0) return LZ4B200_ERR_ARG;
+    if (nBlocks == 0) return LZ4B200_OK;
+    if (!d_src || !d_srcOff || !d_srcSize || !d_dst || !d_outSize || !d_workspace) return LZ4B200_ERR_ARG;
+    if (workspaceBytes < lz4k_decode_workspace_bytes(nBlocks)) return LZ4B200_ERR_ARG;
+    a.src = (const uint8_t*)d_src; a.srcOff = d_srcOff; a.srcSize = d_srcSize;
+    a.dst = (uint8_t*)d_dst; a.dstOff = d_dstOff; a.dstStride = dstStride;
+    a.dstCapArr = d_dstCap; a.dstCap = dstCap; a.outSize = d_outSize; a.nBlocks = nBlocks;
+    a.workspace = d_workspace; a.workspaceBytes = workspaceBytes;
+    e = (cudaError_t)lz4k_launch_decode(&a, stream);
+    return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "lz4k_launch_decode");
+}
+
+int LZ4B200_compress_blocks(const void* d_src, int64_t srcStride, const int32_t* d_srcSize, int32_t srcSize,
+                            void* d_dst, int64_t dstStride, int32_t dstCap, int acceleration,
+                            int32_t* d_outSize, int64_t nBlocks, void* stream)
+{
+    lz4k_encode_args a;
+    cudaError_t e;
+    if (nBlocks < 0) return LZ4B200_ERR_ARG;
+    if (nBlocks == 0) return LZ4B200_OK;
+    if (!d_dst || !d_outSize) return LZ4B200_ERR_ARG;
+    a.src = (const uint8_t*)d_src; a.srcStride = srcStride; a.srcSizeArr = d_srcSize; a.srcSize = srcSize;
+    a.dst = (uint8_t*)d_dst; a.dstStride = dstStride; a.dstCap = dstCap; a.acceleration = acceleration;
+    a.outSize = d_outSize; a.nBlocks = nBlocks;
+    e = (cudaError_t)lz4k_launch_encode(&a, stream);
+    return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "lz4k_launch_encode");
+}
+
+int LZ4B200_pack_blocks(const void* d_slots, int64_t slotStride, const int32_t* d_sizes, int64_t nBlocks,
+                        void* d_packed, int64_t* d_outOff, int headerBytes, void* stream)
+{
+    cudaError_t e;
+    if (nBlocks < 0 || !d_outOff || (headerBytes != 0 && headerBytes != 4)) return LZ4B200_ERR_ARG;
+    if (nBlocks > 0 && (!d_slots || !d_sizes || !d_packed)) return LZ4B200_ERR_ARG;
+    e = (cudaError_t)lz4k_launch_pack((const uint8_t*)d_slots, slotStride, d_sizes, nBlocks, (uint8_t*)d_packed,
+                                      d_outOff, headerBytes, stream);
+    return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "lz4k_launch_pack");
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* host-buffer batch calls: H2D -> kernels -> D2H, N_PIPE chunks in flight                     */
+/* ------------------------------------------------------------------------------------------ */
+#define CHUNK_OUT_BYTES ((int64_t)256 << 20)   /* target decoded bytes per pipeline chunk */
+
+int LZ4B200_decompress_blocks_host(const void* h_src, const int64_t* h_srcOff, const int32_t* h_srcSize,
+                                   void* h_dst, int64_t dstStride, int32_t dstCap,
+                                   int32_t* h_outSize, int64_t nBlocks)
+{
+    int rc = LZ4B200_OK;
+    int64_t perChunk, first;
+    int slot = 0, i;
+    if (nBlocks < 0 || dstCap < 0 || dstStride < dstCap) return LZ4B200_ERR_ARG;
+    if (nBlocks == 0) return LZ4B200_OK;
+    if (!h_src || !h_srcOff || !h_srcSize || !h_dst || !h_outSize) return LZ4B200_ERR_ARG;
+    pthread_mutex_lock(&g_lock);
+    if ((rc = ctx_init()) != LZ4B200_OK) goto done;
+
+    perChunk = CHUNK_OUT_BYTES / (dstStride > 0 ? dstStride : 1);
+    if (perChunk < 1) perChunk = 1;
+    for (first = 0; first < nBlocks; first += perChunk, slot = (slot + 1) % N_PIPE) {
+        const int64_t cnt = (nBlocks - first < perChunk) ? nBlocks - first : perChunk;
+        cudaStream_t st = g_ctx.stream[slot];
+        int64_t lo = h_srcOff[first], hi = lo, k;
+        size_t inBytes, outBytes = (size_t)(cnt * dstStride), metaBytes, wsBytes;
+        int64_t* relOff;
+        /* the chunk's compressed bytes span [lo, hi) of h_src (blocks may be in any order) */
+        for (k = first; k < first + cnt; k++) {
+            if (h_srcSize[k] < 0) { rc = LZ4B200_ERR_ARG; goto done; }
+            if (h_srcOff[k] < lo) lo = h_srcOff[k];
+            if (h_srcOff[k] + h_srcSize[k] > hi) hi = h_srcOff[k] + h_srcSize[k];
+        }
+        inBytes = (size_t)(hi - lo);
+        metaBytes = (size_t)cnt * (sizeof(int64_t) + 2 * sizeof(int32_t));
+        wsBytes = lz4k_decode_workspace_bytes(cnt);
+        CU(cudaStreamSynchronize(st));                      /* slot reuse: previous chunk on it is finished */
+        if ((rc = grow(&g_ctx.d_in[slot], &g_ctx.in_cap[slot], inBytes + 16)) != LZ4B200_OK) goto done;
+        if ((rc = grow(&g_ctx.d_out[slot], &g_ctx.out_cap[slot], outBytes + 16)) != LZ4B200_OK) goto done;
+        if ((rc = grow(&g_ctx.d_meta[slot], &g_ctx.meta_cap[slot], metaBytes + 16)) != LZ4B200_OK) goto done;
+        if ((rc = grow(&g_ctx.d_ws[slot], &g_ctx.ws_cap[slot], wsBytes)) != LZ4B200_OK) goto done;
+        {
+            int64_t* d_off = (int64_t*)g_ctx.d_meta[slot];
+            int32_t* d_size = (int32_t*)(d_off + cnt);
+            int32_t* d_ret = d_size + cnt;
+            /* offsets relative to the chunk's first byte: staged through the (pageable) output-size
+             * array is not possible, so rebase on the fly into a small host vector */
+            relOff = (int64_t*)malloc((size_t)cnt * sizeof(int64_t));
+            if (!relOff) { rc = LZ4B200_ERR_ARG; goto done; }
+            for (k = 0; k < cnt; k++) relOff[k] = h_srcOff[first + k] - lo;
+            CU(cudaMemcpyAsync(d_off, relOff, (size_t)cnt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));                  /* relOff is pageable: copy done before free */
+            free(relOff);
+            CU(cudaMemcpyAsync(d_size, h_srcSize + first, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(g_ctx.d_in[slot], (const char*)h_src + lo, inBytes, cudaMemcpyHostToDevice, st));
+            rc = LZ4B200_decompress_blocks(g_ctx.d_in[slot], d_off, d_size, g_ctx.d_out[slot], NULL, dstStride,
+                                           NULL, dstCap, d_ret, cnt, g_ctx.d_ws[slot], g_ctx.ws_cap[slot], st);
+            if (rc != LZ4B200_OK) goto done;
+            CU(cudaMemcpyAsync((char*)h_dst + first * dstStride, g_ctx.d_out[slot], outBytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_outSize + first, d_ret, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (i = 0; i < N_PIPE; i++) CU(cudaStreamSynchronize(g_ctx.stream[i]));
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int LZ4B200_compress_blocks_host(const void* h_src, int64_t srcStride, int32_t srcSize, int64_t lastSize,
+                                 void* h_dst, int64_t dstStride, int32_t dstCap, int acceleration,
+                                 int32_t* h_outSize, int64_t nBlocks)
+{
+    int rc = LZ4B200_OK;
+    int64_t perChunk, first;
+    int slot = 0, i;
+    if (nBlocks < 0 || srcSize < 0 || lastSize < 0 || lastSize > srcSize || srcStride < srcSize) return LZ4B200_ERR_ARG;
+    if (nBlocks == 0) return LZ4B200_OK;
+    if (!h_dst || !h_outSize || (!h_src && srcSize > 0)) return LZ4B200_ERR_ARG;
+    pthread_mutex_lock(&g_lock);
+    if ((rc = ctx_init()) != LZ4B200_OK) goto done;
+
+    perChunk = CHUNK_OUT_BYTES / (srcStride > 0 ? srcStride : 1);
+    if (perChunk < 1) perChunk = 1;
+    for (first = 0; first < nBlocks; first += perChunk, slot = (slot + 1) % N_PIPE) {
+        const int64_t cnt = (nBlocks - first < perChunk) ? nBlocks - first : perChunk;
+        const int isLast = (first + cnt == nBlocks);
+        cudaStream_t st = g_ctx.stream[slot];
+        size_t inBytes = (size_t)((cnt - 1) * srcStride + (isLast ? lastSize : srcSize));
+        size_t slotBytes = (size_t)(cnt * dstStride);
+        size_t metaBytes = (size_t)cnt * 2 * sizeof(int32_t);
+        int32_t* d_sizes; int32_t* d_ret;
+        CU(cudaStreamSynchronize(st));
+        if ((rc = grow(&g_ctx.d_in[slot], &g_ctx.in_cap[slot], inBytes + 16)) != LZ4B200_OK) goto done;
+        if ((rc = grow(&g_ctx.d_out[slot], &g_ctx.out_cap[slot], slotBytes + 16)) != LZ4B200_OK) goto done;
+        if ((rc = grow(&g_ctx.d_meta[slot], &g_ctx.meta_cap[slot], metaBytes + 16)) != LZ4B200_OK) goto done;
+        d_sizes = (int32_t*)g_ctx.d_meta[slot];
+        d_ret = d_sizes + cnt;
+        if (inBytes) CU(cudaMemcpyAsync(g_ctx.d_in[slot], (const char*)h_src + first * srcStride, inBytes, cudaMemcpyHostToDevice, st));
+        if (isLast && lastSize != srcSize) {
+            /* per-block size table only needed for the ragged final block */
+            int32_t* tmp = (int32_t*)malloc((size_t)cnt * sizeof(int32_t));
+            int64_t k;
+            if (!tmp) { rc = LZ4B200_ERR_ARG; goto done; }
+            for (k = 0; k < cnt; k++) tmp[k] = srcSize;
+            tmp[cnt - 1] = (int32_t)lastSize;
+            CU(cudaMemcpyAsync(d_sizes, tmp, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+            free(tmp);
+            rc = LZ4B200_compress_blocks(g_ctx.d_in[slot], srcStride, d_sizes, srcSize, g_ctx.d_out[slot], dstStride,
+                                         dstCap, acceleration, d_ret, cnt, st);
+        } else {
+            rc = LZ4B200_compress_blocks(g_ctx.d_in[slot], srcStride, NULL, srcSize, g_ctx.d_out[slot], dstStride,
+                                         dstCap, acceleration, d_ret, cnt, st);
+        }
+        if (rc != LZ4B200_OK) goto done;
+        CU(cudaMemcpyAsync((char*)h_dst + first * dstStride, g_ctx.d_out[slot], slotBytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_outSize + first, d_ret, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    for (i = 0; i < N_PIPE; i++) CU(cudaStreamSynchronize(g_ctx.stream[i]));
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* drop-in layer: one block, host pointers, synchronous                                        */
+/* ------------------------------------------------------------------------------------------ */
+static int one_block_compress(const char* src, char* dst, int srcSize, int dstCapacity, int acceleration)
+{
+    int rc = LZ4B200_OK, ret = 0;
+    int32_t* d_ret;
+    cudaStream_t st;
+    size_t capBytes;
+    /* argument rules of LZ4_compress_generic, lz4.c:1360-1372, decided on the host so that a bad
+     * size never reaches the device */
+    if ((unsigned)srcSize > (unsigned)LZ4B200_MAX_INPUT_SIZE) return 0;
+    if (dstCapacity <= 0) return 0;          /* nothing can be written (lz4.c:1362 and the limited checks) */
+    if (dst == NULL) return 0;
+    if (srcSize > 0 && src == NULL) return 0;
+    pthread_mutex_lock(&g_lock);
+    if ((rc = ctx_init()) != LZ4B200_OK) goto done;
+    st = g_ctx.stream[0];
+    {
+        int bound = LZ4_compressBound(srcSize);
+        capBytes = (size_t)(dstCapacity < bound ? dstCapacity : bound);
+    }
+    if ((rc = grow(&g_ctx.d_in[0], &g_ctx.in_cap[0], (size_t)srcSize + 16)) != LZ4B200_OK) goto done;
+    if ((rc = grow(&g_ctx.d_out[0], &g_ctx.out_cap[0], capBytes + 16)) != LZ4B200_OK) goto done;
+    if ((rc = grow(&g_ctx.d_meta[0], &g_ctx.meta_cap[0], 64)) != LZ4B200_OK) goto done;
+    d_ret = (int32_t*)g_ctx.d_meta[0];
+    /* copy-in completes before any output is produced: in-place calls (lz4.h:619-678) are safe */
+    if (srcSize) CU(cudaMemcpyAsync(g_ctx.d_in[0], src, (size_t)srcSize, cudaMemcpyHostToDevice, st));
+    rc = LZ4B200_compress_blocks(g_ctx.d_in[0], 0, NULL, srcSize, g_ctx.d_out[0], 0, dstCapacity, acceleration, d_ret, 1, st);
+    if (rc != LZ4B200_OK) goto done;
+    CU(cudaMemcpyAsync(&ret, d_ret, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ret > 0) {
+        CU(cudaMemcpyAsync(dst, g_ctx.d_out[0], (size_t)ret, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc == LZ4B200_OK ? ret : 0;
+}
+
+int LZ4_compress_fast(const char* src, char* dst, int srcSize, int dstCapacity, int acceleration)
+{
+    return one_block_compress(src, dst, srcSize, dstCapacity, acceleration);
+}
+
+int LZ4_compress_default(const char* src, char* dst, int srcSize, int dstCapacity)
+{
+    return one_block_compress(src, dst, srcSize, dstCapacity, 1);
+}
+
+static int state_is_valid(const void* state)
+{
+    /* LZ4_initStream, lz4.c:1552-1560: non-NULL and aligned like LZ4_stream_t (8 bytes) */
+    return state != NULL && (((uintptr_t)state) & 7u) == 0;
+}
+
+int LZ4_compress_fast_extState(void* state, const char* src, char* dst, int srcSize, int dstCapacity, int acceleration)
+{
+    if (!state_is_valid(state)) return 0;
+    return one_block_compress(src, dst, srcSize, dstCapacity, acceleration);
+}
+
+int LZ4_compress_fast_extState_fastReset(void* state, const char* src, char* dst, int srcSize, int dstCapacity, int acceleration)
+{
+    if (!state_is_valid(state)) return 0;
+    return one_block_compress(src, dst, srcSize, dstCapacity, acceleration);
+}
+
+int LZ4_decompress_safe(const char* src, char* dst, int compressedSize, int dstCapacity)
+{
+    int rc = LZ4B200_OK, ret = -1;
+    cudaStream_t st;
+    int64_t* d_off; int32_t* d_size; int32_t* d_ret;
+    int64_t zero = 0;
+    /* lz4.c:2036, :2064-2069 decided on the host */
+    if (src == NULL || dstCapacity < 0) return -1;
+    if (dstCapacity == 0) return (compressedSize == 1 && src[0] == 0) ? 0 : -1;
+    if (compressedSize <= 0) return -1;
+    if (dst == NULL) return -1;
+    pthread_mutex_lock(&g_lock);
+    if ((rc = ctx_init()) != LZ4B200_OK) goto done;
+    st = g_ctx.stream[0];
+    if ((rc = grow(&g_ctx.d_in[0], &g_ctx.in_cap[0], (size_t)compressedSize + 16)) != LZ4B200_OK) goto done;
+    if ((rc = grow(&g_ctx.d_out[0], &g_ctx.out_cap[0], (size_t)dstCapacity + 16)) != LZ4B200_OK) goto done;
+    if ((rc = grow(&g_ctx.d_meta[0], &g_ctx.meta_cap[0], 64)) != LZ4B200_OK) goto done;
+    if ((rc = grow(&g_ctx.d_ws[0], &g_ctx.ws_cap[0], lz4k_decode_workspace_bytes(1))) != LZ4B200_OK) goto done;
+    d_off = (int64_t*)g_ctx.d_meta[0];
+    d_size = (int32_t*)(d_off + 1);
+    d_ret = d_size + 1;
+    CU(cudaMemcpyAsync(d_off, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_size, &compressedSize, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    /* the whole input is on the device before the first output byte is written back: in-place
+     * decompression (lz4.h:619-678, tests/fuzzer.c:1177-1187) needs no special handling */
+    CU(cudaMemcpyAsync(g_ctx.d_in[0], src, (size_t)compressedSize, cudaMemcpyHostToDevice, st));
+    rc = LZ4B200_decompress_blocks(g_ctx.d_in[0], d_off, d_size, g_ctx.d_out[0], NULL, 0, NULL, dstCapacity,
+                                   d_ret, 1, g_ctx.d_ws[0], g_ctx.ws_cap[0], st);
+    if (rc != LZ4B200_OK) goto done;
+    CU(cudaMemcpyAsync(&ret, d_ret, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ret > 0) {
+        CU(cudaMemcpyAsync(dst, g_ctx.d_out[0], (size_t)ret, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc == LZ4B200_OK ? ret : -1;
+}
+
+int LZ4_decompress_safe_usingDict(const char* src, char* dst, int compressedSize, int dstCapacity,
+                                  const char* dictStart, int dictSize)
+{
+    (void)dictStart;
+    if (dictSize == 0) return LZ4_decompress_safe(src, dst, compressedSize, dstCapacity);   /* lz4.c:2721-2722 */
+    return -1;   /* prefix / external dictionaries: SURVEY.md section 8 (f-4), not on the GPU path */
+}

@@ -1,0 +1,561 @@
+/*
+ * lz4_kernels.cu -- hand-written sm_100a CUDA kernels of the LZ4 block codec.
+ *
+ * Decode = two kernels:
+ *   scan   : one THREAD per block walks the token chain and applies every acceptance rule of the
+ *            reference decoder (lz4.c:2022-2445, x86-64 control flow incl. the fast loop), giving
+ *            the exact return value.  No data is moved.
+ *   expand : moves the bytes of blocks the scan accepted (literal + match copies).
+ * Encode = one WARP per block replaying the reference's greedy parse (lz4.c:930-1338) with the
+ *   32 lanes probing 32 consecutive search positions per step; output is byte-identical.
+ * pack   = exclusive scan of block sizes + gather into one contiguous stream.
+ *
+ * All arithmetic is integer/byte; no tensor cores (this is an HBM/latency-bound scan codec).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lz4_kernels.h"
+
+namespace {
+
+constexpr int kMinMatch = 4;
+constexpr int kLastLiterals = 5;
+constexpr int kMfLimit = 12;
+constexpr int kMinLength = 13;
+constexpr uint32_t kMaxDistance = 65535;
+constexpr int kSmallLimit = 65536 + 11;          // lz4.c:710
+constexpr int kSkipTrigger = 6;                  // lz4.c:711
+constexpr int kAccelMax = 65537;                 // lz4.c:58
+constexpr uint32_t kMaxInput = 0x7E000000u;      // lz4.h:214
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+unsigned long long g_launches = 0;
+
+__device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return __ldg(p) | (__ldg(p + 1) << 8); }
+
+/* unaligned little-endian 32-bit read through two aligned words (never touches a word that holds
+ * no requested byte) */
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* p)
+{
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t lo = __ldg(w);
+    uint32_t hi = sh ? __ldg(w + 1) : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+/* low 5 bytes at p (for the 5-byte hash, lz4.c:785-791) */
+__device__ __forceinline__ uint64_t ld40u(const uint8_t* p)
+{
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t lo = __ldg(w);
+    uint32_t hi = __ldg(w + 1);
+    uint32_t v = __funnelshift_r(lo, hi, sh);
+    uint32_t b4 = (hi >> sh) & 0xFFu;
+    return (uint64_t)v | ((uint64_t)b4 << 32);
+}
+
+/* =============================================================================================
+ * scan: exact acceptance + return value of LZ4_decompress_safe, one thread per block
+ * ============================================================================================= */
+
+/* lz4.c:1978-2014.  ip advances exactly like the reference's pointer so that the error code
+ * -(ip)-1 (lz4.c:2443) is reproduced. */
+__device__ __forceinline__ bool read_runlength(const uint8_t* src, int64_t& ip, int64_t ilimit, bool initialCheck, int64_t& total)
+{
+    total = 0;
+    if (initialCheck && ip >= ilimit) return false;
+    uint32_t b;
+    do {
+        b = ldb(src + ip);
+        ip++;
+        total += b;
+        if (ip > ilimit) return false;
+    } while (b == 255);
+    return true;
+}
+
+__device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut)
+{
+    int64_t n = nIn, cap = capIn, ip = 0, op = 0, ll = 0, ml = 0, add = 0;
+    uint32_t token = 0, offset = 0, nseq = 0;
+    bool fast;
+
+    if (capIn < 0) return -1;                                          // lz4.c:2036
+    if (capIn == 0) return (nIn == 1 && ldb(src) == 0) ? 0 : -1;       // lz4.c:2064-2068
+    if (nIn <= 0) return -1;                                           // lz4.c:2069
+    fast = (cap >= 64);                                                // lz4.c:2076
+
+    for (;;) {
+        token = ldb(src + ip); ip++;
+        ll = token >> 4;
+        ml = token & 15;
+
+        if (fast) {                                                    // lz4.c:2083-2209
+            if (ll == 15) {
+                if (!read_runlength(src, ip, n - 15, true, add)) goto bad;
+                ll += add;
+                if (op + ll > cap - 32 || ip + ll > n - 32) { fast = false; goto safe_literals; }
+            } else if (ip > n - 17) {
+                fast = false; goto safe_literals;
+            }
+            ip += ll; op += ll;
+            offset = ld16(src + ip); ip += 2;
+            if (ml == 15) {
+                if (!read_runlength(src, ip, n - 4, false, add)) goto bad;
+                ml += add;
+            }
+            ml += kMinMatch;
+            if (op + ml >= cap - 64) { fast = false; goto safe_match; }
+            if ((int64_t)offset > op) goto bad;                        // lz4.c:2161
+            op += ml; nseq++;
+            continue;
+        }
+
+        /* safe loop, lz4.c:2215-2435 */
+        if (ll != 15 && ip < n - 16 && op <= cap - 32) {               // two-stage shortcut :2230-2261
+            op += ll; ip += ll;
+            offset = ld16(src + ip); ip += 2;
+            if (ml != 15 && offset >= 8 && (int64_t)offset <= op) { op += ml + kMinMatch; nseq++; continue; }
+            goto match_length;
+        }
+        if (ll == 15) {
+            if (!read_runlength(src, ip, n - 15, true, add)) goto bad;
+            ll += add;
+        }
+safe_literals:
+        if (op + ll > cap - kMfLimit || ip + ll > n - (2 + 1 + kLastLiterals)) {   // lz4.c:2279
+            if (ip + ll != n || op + ll > cap) goto bad;               // lz4.c:2312
+            op += ll; nseq++;
+            *nSeqOut = nseq;
+            return (int)op;                                            // lz4.c:2439
+        }
+        ip += ll; op += ll;
+        offset = ld16(src + ip); ip += 2;
+match_length:
+        if (ml == 15) {
+            if (!read_runlength(src, ip, n - 4, false, add)) goto bad;
+            ml += add;
+        }
+        ml += kMinMatch;
+safe_match:
+        if ((int64_t)offset > op) goto bad;                            // lz4.c:2356
+        if (op + ml > cap - kLastLiterals) goto bad;                   // lz4.c:2421-2423
+        op += ml; nseq++;
+    }
+bad:
+    *nSeqOut = 0;
+    return (int)(-ip) - 1;                                             // lz4.c:2443
+}
+
+__global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a, uint32_t* __restrict__ nSeq)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.nBlocks) return;
+    const uint8_t* src = a.src + a.srcOff[b];
+    int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
+    uint32_t ns = 0;
+    int r = scan_block(src, a.srcSize[b], cap, &ns);
+    a.outSize[b] = r;
+    nSeq[b] = ns;
+}
+
+/* =============================================================================================
+ * expand (generic): one warp per accepted block, any block size, straight to global memory
+ * ============================================================================================= */
+__global__ void __launch_bounds__(128) lz4_expand_generic_kernel(lz4k_decode_args a)
+{
+    const int lane = threadIdx.x & 31;
+    int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= a.nBlocks) return;
+    const int total = a.outSize[b];
+    if (total <= 0) return;                       // rejected (or empty) block: nothing to write
+    const uint8_t* __restrict__ src = a.src + a.srcOff[b];
+    uint8_t* dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
+    const int64_t n = a.srcSize[b];
+    int64_t ip = 0, op = 0;
+
+    for (;;) {
+        uint32_t token = ldb(src + ip); ip++;
+        int64_t ll = token >> 4;
+        if (ll == 15) { uint32_t x; do { x = ldb(src + ip); ip++; ll += x; } while (x == 255); }
+        for (int64_t k = lane; k < ll; k += 32) dst[op + k] = (uint8_t)ldb(src + ip + k);
+        ip += ll; op += ll;
+        if (ip >= n) break;
+        uint32_t offset = ld16(src + ip); ip += 2;
+        int64_t ml = token & 15;
+        if (ml == 15) { uint32_t x; do { x = ldb(src + ip); ip++; ml += x; } while (x == 255); }
+        ml += kMinMatch;
+        __syncwarp();                             // everything before `op` is now visible to all lanes
+        if (offset == 0) {                        // reference zero-fills (lz4.c:2407, :500)
+            for (int64_t k = lane; k < ml; k += 32) dst[op + k] = 0;
+        } else if ((int64_t)offset >= ml) {
+            const volatile uint8_t* from = dst + op - offset;
+            for (int64_t k = lane; k < ml; k += 32) dst[op + k] = from[k];
+        } else {                                  // self-overlapping match: period `offset`
+            const volatile uint8_t* from = dst + op - offset;
+            for (int64_t k = lane; k < ml; k += 32) dst[op + k] = from[k % offset];
+        }
+        op += ml;
+    }
+}
+
+/* =============================================================================================
+ * encode: one warp per block, byte-identical replay of LZ4_compress_generic_validated
+ * ============================================================================================= */
+
+template <bool SMALL> struct Table;
+template <> struct Table<true> {       // byU16, 13-bit 4-byte hash (lz4.c:779-780)
+    uint16_t* t;
+    __device__ __forceinline__ uint32_t hash(const uint8_t* p) const { return (ld32u(p) * 2654435761u) >> 19; }
+    __device__ __forceinline__ uint32_t hashv(const uint8_t* p, uint32_t& v32) const { v32 = ld32u(p); return (v32 * 2654435761u) >> 19; }
+    __device__ __forceinline__ uint32_t get(uint32_t h) const { return t[h]; }
+    __device__ __forceinline__ void put(uint32_t h, uint32_t pos) const { t[h] = (uint16_t)pos; }
+};
+template <> struct Table<false> {      // byU32, 12-bit 5-byte hash (lz4.c:785-791,799)
+    uint32_t* t;
+    __device__ __forceinline__ static uint32_t h5(uint64_t v) { return (uint32_t)(((v << 24) * 889523592379ull) >> 52); }
+    __device__ __forceinline__ uint32_t hash(const uint8_t* p) const { return h5(ld40u(p)); }
+    __device__ __forceinline__ uint32_t hashv(const uint8_t* p, uint32_t& v32) const { uint64_t v = ld40u(p); v32 = (uint32_t)v; return h5(v); }
+    __device__ __forceinline__ uint32_t get(uint32_t h) const { return t[h]; }
+    __device__ __forceinline__ void put(uint32_t h, uint32_t pos) const { t[h] = pos; }
+};
+
+/* sum_{t<m} (accel + (t >> 6)): distance covered by m search steps after the first one,
+ * from step = (searchMatchNb++ >> LZ4_skipTrigger) with searchMatchNb = accel << 6 (lz4.c:1044-1053) */
+__device__ __forceinline__ uint32_t skip_distance(uint32_t m, uint32_t accel)
+{
+    uint32_t q = m >> kSkipTrigger, r = m & 63u;
+    return accel * m + 32u * q * (q - 1u) + q * r;
+}
+
+/* run-length extension bytes: `len` -> 255,255,...,rem  (lz4.c:1123-1128) written by the warp */
+__device__ __forceinline__ uint32_t emit_runlength(uint8_t* dst, uint32_t op, uint32_t len, int lane)
+{
+    uint32_t full = len / 255u;
+    for (uint32_t k = lane; k < full; k += 32) dst[op + k] = 255;
+    if (lane == 0) dst[op + full] = (uint8_t)(len - full * 255u);
+    return op + full + 1;
+}
+
+template <bool SMALL>
+__device__ int encode_block(const uint8_t* __restrict__ src, const int n, uint8_t* __restrict__ dst,
+                            const int dstCap, const uint32_t accel, void* tableMem, const int lane)
+{
+    Table<SMALL> T;
+    T.t = reinterpret_cast<decltype(T.t)>(tableMem);
+    const int bound = n + n / 255 + 16;
+    const bool limited = !(dstCap >= bound);
+    const int64_t olimit = dstCap;
+    const uint32_t mflimit1 = (uint32_t)n - kMfLimit + 1;     // lz4.c:963
+    const uint32_t matchlimit = (uint32_t)n - kLastLiterals;  // lz4.c:964
+    uint32_t ip = 0, anchor = 0, op = 0, cand = 0;
+
+    {   // zeroed table, lz4.c:1558
+        uint4* z = reinterpret_cast<uint4*>(tableMem);
+        for (int k = lane; k < 1024; k += 32) z[k] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+
+    if (n < kMinLength) goto tail;                            // lz4.c:1002
+
+    if (lane == 0) T.put(T.hash(src), 0);                     // lz4.c:1005-1010
+    __syncwarp();
+    ip = 1;
+
+    for (;;) {
+        /* ---- search: lanes probe the next 32 positions of the reference's visiting order ---- */
+        {
+            uint32_t baseJ = 0;
+            bool found = false;
+            for (;;) {
+                const uint32_t j = baseJ + lane;
+                const uint32_t p = ip + (j ? 1u + skip_distance(j - 1, accel) : 0u);
+                const uint32_t pnext = ip + 1u + skip_distance(j, accel);
+                const bool term = pnext > mflimit1;           // lz4.c:1055 fires at this visit
+                uint32_t v32 = 0, h = 0x80000000u | lane, old = 0;
+                if (!term) { h = T.hashv(src + p, v32); old = T.get(h); }
+                const unsigned peers = __match_any_sync(kFull, h);
+                const unsigned lower = peers & ((1u << lane) - 1u);
+                const int fromLane = lower ? (31 - __clz(lower)) : lane;
+                const uint32_t pPrev = __shfl_sync(kFull, p, fromLane);
+                const uint32_t c = lower ? pPrev : old;       // table value this visit would read
+                bool hit = false;
+                if (!term) {
+                    if (SMALL || c + kMaxDistance >= p) hit = (ld32u(src + c) == v32);   // lz4.c:1090-1096
+                }
+                const unsigned termMask = __ballot_sync(kFull, term);
+                const unsigned hitMask = __ballot_sync(kFull, hit);
+                const int firstTerm = termMask ? (__ffs(termMask) - 1) : 32;
+                const int firstHit = hitMask ? (__ffs(hitMask) - 1) : 32;
+                if (firstHit < firstTerm) {
+                    /* visits 0..firstHit happened: each stored its position (lz4.c:1085); for equal
+                     * hashes the latest visit wins */
+                    const unsigned upto = (firstHit == 31) ? kFull : ((2u << firstHit) - 1u);
+                    const unsigned mine = peers & upto;
+                    if (lane <= firstHit && (mine >> lane) == 1u) T.put(h, p);
+                    ip = __shfl_sync(kFull, p, firstHit);
+                    cand = __shfl_sync(kFull, c, firstHit);
+                    found = true;
+                    __syncwarp();
+                    break;
+                }
+                if (firstTerm < 32) break;                    // goto _last_literals
+                if ((peers >> lane) == 1u) T.put(h, p);
+                __syncwarp();
+                baseJ += 32;
+            }
+            if (!found) goto tail;
+        }
+
+        /* ---- backward extension (lz4.c:1107-1109) ---- */
+        for (;;) {
+            const uint32_t room = min(ip - anchor, cand);
+            const uint32_t k = lane + 1;
+            const bool eq = (k <= room) && (ldb(src + ip - k) == ldb(src + cand - k));
+            const unsigned m = __ballot_sync(kFull, eq);
+            const uint32_t run = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
+            ip -= run; cand -= run;
+            if (run < 32) break;
+        }
+
+        {
+            uint32_t lit = ip - anchor;
+            bool haveLiterals = true;
+            for (;;) {   /* the _next_match chain, lz4.c:1138-1294 */
+                /* match length first (the token needs it): LZ4_count, lz4.c:1182 */
+                uint32_t mcode = 0;
+                {
+                    const uint8_t* pa = src + ip + kMinMatch;
+                    const uint8_t* pb = src + cand + kMinMatch;
+                    const uint32_t lim = matchlimit - (ip + kMinMatch);    // bytes comparable
+                    for (uint32_t base = 0;; base += 32) {
+                        const uint32_t k = base + lane;
+                        const bool eq = (k < lim) && (ldb(pa + k) == ldb(pb + k));
+                        const unsigned m = __ballot_sync(kFull, eq);
+                        if (m != kFull) { mcode = base + (uint32_t)(__ffs(~m) - 1); break; }
+                    }
+                }
+                const uint32_t tokenPos = op;
+                uint32_t o = op + 1;
+                if (haveLiterals) {
+                    /* lz4.c:1114-1117 */
+                    if (limited && (int64_t)o + lit + (2 + 1 + kLastLiterals) + lit / 255 > olimit) return 0;
+                    if (lit >= 15) o = emit_runlength(dst, o, lit - 15, lane);
+                    for (uint32_t k = lane; k < lit; k += 32) dst[o + k] = (uint8_t)ldb(src + anchor + k);
+                    o += lit;
+                }
+                /* offset, lz4.c:1162 */
+                const uint32_t off = ip - cand;
+                if (lane == 0) { dst[o] = (uint8_t)off; dst[o + 1] = (uint8_t)(off >> 8); }
+                o += 2;
+                /* lz4.c:1187-1211 */
+                if (limited && (int64_t)o + (1 + kLastLiterals) + (mcode + 240) / 255 > olimit) return 0;
+                if (lane == 0) {
+                    const uint32_t lt = haveLiterals ? min(lit, 15u) : 0u;
+                    dst[tokenPos] = (uint8_t)((lt << 4) | min(mcode, 15u));
+                }
+                if (mcode >= 15) o = emit_runlength(dst, o, mcode - 15, lane);   // lz4.c:1213-1223
+                op = o;
+
+                ip += mcode + kMinMatch;
+                anchor = ip;
+                if (ip >= mflimit1) goto tail;                         // lz4.c:1233
+
+                if (lane == 0) T.put(T.hash(src + ip - 2), ip - 2);    // lz4.c:1236-1242
+                __syncwarp();
+                {   /* immediate re-test at ip, lz4.c:1255-1294 */
+                    uint32_t v32;
+                    const uint32_t h = T.hashv(src + ip, v32);
+                    cand = T.get(h);
+                    __syncwarp();
+                    if (lane == 0) T.put(h, ip);
+                    __syncwarp();
+                    if ((SMALL || cand + kMaxDistance >= ip) && ld32u(src + cand) == v32) {
+                        haveLiterals = false; lit = 0;
+                        continue;
+                    }
+                }
+                break;
+            }
+        }
+        ip++;                                                          // lz4.c:1298
+    }
+
+tail:   /* lz4.c:1302-1329 */
+    {
+        const uint32_t last = (uint32_t)n - anchor;
+        if (limited && (int64_t)op + last + 1 + (last + 255 - 15) / 255 > olimit) return 0;
+        uint32_t o = op + 1;
+        if (lane == 0) dst[op] = (uint8_t)(min(last, 15u) << 4);
+        if (last >= 15) o = emit_runlength(dst, o, last - 15, lane);
+        for (uint32_t k = lane; k < last; k += 32) dst[o + k] = (uint8_t)ldb(src + anchor + k);
+        return (int)(o + last);
+    }
+}
+
+constexpr int kEncodeTableBytes = 16384;    // LZ4_HASHTABLESIZE, lz4.h:157-172 (LZ4_MEMORY_USAGE 14)
+
+__global__ void __launch_bounds__(32) lz4_encode_kernel(lz4k_encode_args a)
+{
+    extern __shared__ uint4 tableMem[];
+    const int lane = threadIdx.x;
+    uint32_t accel = a.acceleration < 1 ? 1u : (a.acceleration > kAccelMax ? (uint32_t)kAccelMax : (uint32_t)a.acceleration);  // lz4.c:1386-1387
+    for (int64_t b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
+        const uint8_t* src = a.src + b * a.srcStride;
+        uint8_t* dst = a.dst + b * a.dstStride;
+        const int n = a.srcSizeArr ? a.srcSizeArr[b] : a.srcSize;
+        int r;
+        if ((uint32_t)n > kMaxInput) {                                  // lz4.c:1360
+            r = 0;
+        } else if (n == 0) {                                            // lz4.c:1361-1371
+            const bool limited = !(a.dstCap >= 16);
+            if (limited && a.dstCap <= 0) r = 0;
+            else { if (lane == 0) dst[0] = 0; r = 1; }
+        } else if (n < kSmallLimit) {                                   // lz4.c:1389
+            r = encode_block<true>(src, n, dst, a.dstCap, accel, tableMem, lane);
+        } else {
+            r = encode_block<false>(src, n, dst, a.dstCap, accel, tableMem, lane);
+        }
+        if (lane == 0) a.outSize[b] = r;
+        __syncwarp();
+    }
+}
+
+/* =============================================================================================
+ * pack: exclusive scan of sizes (+ optional 4-byte headers) and gather into a contiguous stream
+ * ============================================================================================= */
+__global__ void __launch_bounds__(1024) lz4_pack_scan_kernel(const int32_t* __restrict__ sizes, int64_t n,
+                                                             int64_t* __restrict__ outOff, int headerBytes)
+{
+    __shared__ int64_t warpSums[32];
+    __shared__ int64_t carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        int64_t v = 0;
+        if (i < n) { int s = sizes[i]; v = (s > 0 ? s : 0) + headerBytes; }
+        int64_t x = v;
+        for (int d = 1; d < 32; d <<= 1) { int64_t y = __shfl_up_sync(kFull, x, d); if (lane >= d) x += y; }
+        if (lane == 31) warpSums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int64_t w = warpSums[lane];
+            for (int d = 1; d < 32; d <<= 1) { int64_t y = __shfl_up_sync(kFull, w, d); if (lane >= d) w += y; }
+            warpSums[lane] = w;
+        }
+        __syncthreads();
+        int64_t prefix = carry + (wid ? warpSums[wid - 1] : 0) + x - v;
+        if (i < n) outOff[i] = prefix;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) outOff[n] = carry;
+}
+
+__global__ void __launch_bounds__(256) lz4_pack_gather_kernel(const uint8_t* __restrict__ slots, int64_t slotStride,
+                                                              const int32_t* __restrict__ sizes, int64_t n,
+                                                              uint8_t* __restrict__ packed, const int64_t* __restrict__ outOff,
+                                                              int headerBytes)
+{
+    for (int64_t b = blockIdx.x; b < n; b += gridDim.x) {
+        const int s = sizes[b] > 0 ? sizes[b] : 0;
+        const uint8_t* from = slots + b * slotStride;
+        uint8_t* to = packed + outOff[b];
+        if (headerBytes == 4 && threadIdx.x < 4) to[threadIdx.x] = (uint8_t)((uint32_t)s >> (8 * threadIdx.x));   // lz4frame.c:896-907 LE32
+        to += headerBytes;
+        /* destination-aligned 16-byte stores, source read through aligned words */
+        const uintptr_t ta = reinterpret_cast<uintptr_t>(to);
+        int head = (int)((16 - (ta & 15)) & 15);
+        if (head > s) head = s;
+        for (int k = threadIdx.x; k < head; k += blockDim.x) to[k] = from[k];
+        const int body = (s - head) >> 4;
+        const uint8_t* fb = from + head;
+        uint4* tb = reinterpret_cast<uint4*>(to + head);
+        const uintptr_t fa = reinterpret_cast<uintptr_t>(fb);
+        const uint32_t sh = (uint32_t)(fa & 3) * 8;
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(fa & ~uintptr_t(3));
+        for (int k = threadIdx.x; k < body; k += blockDim.x) {
+            const uint32_t* w = fw + 4 * k;
+            uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+            uint32_t w4 = sh ? __ldg(w + 4) : 0u;
+            uint4 v;
+            v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+            v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+            tb[k] = v;
+        }
+        for (int k = head + (body << 4) + threadIdx.x; k < s; k += blockDim.x) to[k] = from[k];
+    }
+}
+
+}  // namespace
+
+/* =============================================================================================
+ * extern "C" launchers
+ * ============================================================================================= */
+extern "C" {
+
+uint64_t lz4k_launch_count(void) { return g_launches; }
+
+size_t lz4k_decode_workspace_bytes(int64_t nBlocks)
+{
+    if (nBlocks < 0) return 0;
+    return (size_t)nBlocks * sizeof(uint32_t) + 256;
+}
+
+int lz4k_launch_decode(const lz4k_decode_args* a, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->nBlocks == 0) return 0;
+    uint32_t* nSeq = reinterpret_cast<uint32_t*>(a->workspace);
+    {
+        const int threads = 128;
+        const int64_t grid = (a->nBlocks + threads - 1) / threads;
+        lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a, nSeq);
+        g_launches++;
+    }
+    {
+        const int threads = 128;   // 4 warps = 4 blocks per CTA
+        const int64_t grid = (a->nBlocks * 32 + threads - 1) / threads;
+        lz4_expand_generic_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
+        g_launches++;
+    }
+    return (int)cudaGetLastError();
+}
+
+int lz4k_launch_encode(const lz4k_encode_args* a, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->nBlocks == 0) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int perSm = 13;    // 16 KB table per warp: 13 x 16 KB + reserved fits the 228 KB SM
+    int64_t grid = (int64_t)sms * perSm;
+    if (grid > a->nBlocks) grid = a->nBlocks;
+    lz4_encode_kernel<<<(unsigned)grid, 32, kEncodeTableBytes, s>>>(*a);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int lz4k_launch_pack(const uint8_t* slots, int64_t slotStride, const int32_t* sizes, int64_t nBlocks,
+                     uint8_t* packed, int64_t* outOff, int headerBytes, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    lz4_pack_scan_kernel<<<1, 1024, 0, s>>>(sizes, nBlocks, outOff, headerBytes);
+    g_launches++;
+    if (nBlocks > 0) {
+        int64_t grid = nBlocks < 148 * 16 ? nBlocks : 148 * 16;
+        lz4_pack_gather_kernel<<<(unsigned)grid, 256, 0, s>>>(slots, slotStride, sizes, nBlocks, packed, outOff, headerBytes);
+        g_launches++;
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
