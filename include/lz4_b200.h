@@ -106,6 +106,18 @@ LZ4B200_API int LZ4B200_decompress_blocks(const void* d_src, const int64_t* d_sr
                                           void* d_workspace, size_t workspaceBytes, void* stream);
 
 /*
+ * The same call split in its two phases (phases: 1 = scan only -- validate every block and fill
+ * d_outSize with the decoded sizes / error codes without moving data, the batched equivalent of
+ * asking "what would LZ4_decompress_safe return"; 2 = expand only -- move the bytes of the
+ * blocks a previous scan accepted, same arguments and workspace; 3 = both).
+ */
+LZ4B200_API int LZ4B200_decompress_blocks_phased(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
+                                                 void* d_dst, const int64_t* d_dstOff, int64_t dstStride,
+                                                 const int32_t* d_dstCap, int32_t dstCap,
+                                                 int32_t* d_outSize, int64_t nBlocks,
+                                                 void* d_workspace, size_t workspaceBytes, int phases, void* stream);
+
+/*
  * Compress nBlocks independent blocks (the batched LZ4_compress_fast; replaces bench.c:464-493 and
  * lz4frame.c:1046-1055).
  *   block i input : d_src + i*srcStride, size (d_srcSize ? d_srcSize[i] : srcSize)

@@ -24,7 +24,7 @@ def compress_bound(n):
 
 
 def decompress_blocks(comp, offsets, sizes, block_capacity, out=None, out_stride=None, out_sizes=None,
-                      workspace=None, stream=None):
+                      workspace=None, stream=None, phases=3):
     """Decode len(sizes) independent blocks.
 
     comp: u8[*] device buffer; block i = comp[offsets[i] : offsets[i]+sizes[i]] (int64 / int32 device
@@ -43,9 +43,10 @@ def decompress_blocks(comp, offsets, sizes, block_capacity, out=None, out_stride
     if workspace is None or workspace.numel() < ws_bytes:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=comp.device)
     assert offsets.dtype == torch.int64 and sizes.dtype == torch.int32 and comp.dtype == torch.uint8
-    rc = lib.LZ4B200_decompress_blocks(comp.data_ptr(), offsets.data_ptr(), sizes.data_ptr(), out.data_ptr(), None,
-                                       stride, None, int(block_capacity), out_sizes.data_ptr(), n,
-                                       workspace.data_ptr(), workspace.numel(), _stream_ptr(stream))
+    rc = lib.LZ4B200_decompress_blocks_phased(comp.data_ptr(), offsets.data_ptr(), sizes.data_ptr(), out.data_ptr(),
+                                              None, stride, None, int(block_capacity), out_sizes.data_ptr(), n,
+                                              workspace.data_ptr(), workspace.numel(), int(phases),
+                                              _stream_ptr(stream))
     _lib.check(rc, "LZ4B200_decompress_blocks")
     return out, out_sizes
 

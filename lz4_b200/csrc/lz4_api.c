@@ -94,11 +94,11 @@ done:
 /* ------------------------------------------------------------------------------------------ */
 size_t LZ4B200_decompress_workspace_bytes(int64_t nBlocks) { return lz4k_decode_workspace_bytes(nBlocks); }
 
-int LZ4B200_decompress_blocks(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
+int LZ4B200_decompress_blocks_phased(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
                               void* d_dst, const int64_t* d_dstOff, int64_t dstStride,
                               const int32_t* d_dstCap, int32_t dstCap,
                               int32_t* d_outSize, int64_t nBlocks,
-                              void* d_workspace, size_t workspaceBytes, void* stream)
+                              void* d_workspace, size_t workspaceBytes, int phases, void* stream)
 {
     lz4k_decode_args a;
     cudaError_t e;
@@ -110,8 +110,19 @@ int LZ4B200_decompress_blocks(const void* d_src, const int64_t* d_srcOff, const 
     a.dst = (uint8_t*)d_dst; a.dstOff = d_dstOff; a.dstStride = dstStride;
     a.dstCapArr = d_dstCap; a.dstCap = dstCap; a.outSize = d_outSize; a.nBlocks = nBlocks;
     a.workspace = d_workspace; a.workspaceBytes = workspaceBytes;
-    e = (cudaError_t)lz4k_launch_decode(&a, stream);
+    if (phases < 1 || phases > 3) return LZ4B200_ERR_ARG;
+    e = (cudaError_t)lz4k_launch_decode(&a, phases, stream);
     return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "lz4k_launch_decode");
+}
+
+int LZ4B200_decompress_blocks(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
+                              void* d_dst, const int64_t* d_dstOff, int64_t dstStride,
+                              const int32_t* d_dstCap, int32_t dstCap,
+                              int32_t* d_outSize, int64_t nBlocks,
+                              void* d_workspace, size_t workspaceBytes, void* stream)
+{
+    return LZ4B200_decompress_blocks_phased(d_src, d_srcOff, d_srcSize, d_dst, d_dstOff, dstStride, d_dstCap, dstCap,
+                                            d_outSize, nBlocks, d_workspace, workspaceBytes, 3, stream);
 }
 
 int LZ4B200_compress_blocks(const void* d_src, int64_t srcStride, const int32_t* d_srcSize, int32_t srcSize,

@@ -509,18 +509,18 @@ size_t lz4k_decode_workspace_bytes(int64_t nBlocks)
     return (size_t)nBlocks * sizeof(uint32_t) + 256;
 }
 
-int lz4k_launch_decode(const lz4k_decode_args* a, void* stream)
+int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (a->nBlocks == 0) return 0;
     uint32_t* nSeq = reinterpret_cast<uint32_t*>(a->workspace);
-    {
+    if (phases & 1) {
         const int threads = 128;
         const int64_t grid = (a->nBlocks + threads - 1) / threads;
         lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a, nSeq);
         g_launches++;
     }
-    {
+    if (phases & 2) {
         const int threads = 128;   // 4 warps = 4 blocks per CTA
         const int64_t grid = (a->nBlocks * 32 + threads - 1) / threads;
         lz4_expand_generic_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);

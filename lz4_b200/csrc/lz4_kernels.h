@@ -42,7 +42,8 @@ typedef struct {
 } lz4k_encode_args;
 
 size_t lz4k_decode_workspace_bytes(int64_t nBlocks);
-int lz4k_launch_decode(const lz4k_decode_args* a, void* stream);
+/* phases: bit 0 = scan (validate, sizes), bit 1 = expand (move bytes; needs a prior scan's outSize) */
+int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream);
 int lz4k_launch_encode(const lz4k_encode_args* a, void* stream);
 int lz4k_launch_pack(const uint8_t* slots, int64_t slotStride, const int32_t* sizes, int64_t nBlocks,
                      uint8_t* packed, int64_t* outOff, int headerBytes, void* stream);

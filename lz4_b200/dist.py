@@ -1,0 +1,68 @@
+"""Multi-GPU plumbing: block sharding across ranks and NCCL all-gather reassembly.
+
+Blocks are independent units: rank r of R owns the contiguous block range
+[r*N/R, (r+1)*N/R).  The codec itself needs no communication; the only exchange step is the
+reassembly of the frame: one in-place all-gather of the fixed-size decoded shards, or -- for
+compressed output -- an all-gather of the int32 size table followed by an all-gather of the
+shards padded to the largest one.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the
+transport; nothing here touches the bytes.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_blocks, rank, world):
+    """Contiguous block range [lo, hi) owned by `rank` (sizes differ by at most one block)."""
+    lo = n_blocks * rank // world
+    hi = n_blocks * (rank + 1) // world
+    return lo, hi
+
+
+def _all_gather_flat(out, shard, group=None):
+    """all_gather_into_tensor where the backend has it (NCCL), list all_gather otherwise (gloo)."""
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, shard, group=group)
+    else:
+        chunks = list(out.view(world, -1).unbind(0))
+        dist.all_gather(chunks, shard, group=group)
+    return out
+
+
+def allgather_decoded(full, n_blocks, block_size, group=None):
+    """Reassemble a decoded frame: every rank decoded its shard INTO ITS SLICE of `full`
+    (u8[n_blocks*block_size]); after the call every rank holds the whole frame.
+
+    Requires n_blocks % world == 0 (equal shards => one in-place all-gather, no padding)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if n_blocks % world:
+        raise ValueError("allgather_decoded needs n_blocks divisible by the world size")
+    per = n_blocks // world * block_size
+    shard = full[rank * per:(rank + 1) * per]
+    return _all_gather_flat(full[:world * per], shard, group)
+
+
+def allgather_compressed(packed, total_bytes, sizes, group=None):
+    """Reassemble a compressed frame from per-rank packed shards.
+
+    packed: this rank's contiguous compressed bytes (u8, at least total_bytes long);
+    sizes : int32[blocks_per_rank] compressed size of each local block (same count on all ranks).
+    Returns (all_sizes int32[R*blocks_per_rank], shards u8[R, max_shard], shard_bytes int64[R]):
+    rank r's bytes are shards[r, :shard_bytes[r]]; concatenated in rank order they are the frame's
+    block payloads in block order (the ordered-writer role of lz4io.c:594-635).
+    """
+    world = dist.get_world_size(group)
+    dev = packed.device
+    all_sizes = torch.empty(world * sizes.numel(), dtype=torch.int32, device=dev)
+    _all_gather_flat(all_sizes, sizes.contiguous(), group)
+    mine = torch.tensor([int(total_bytes)], dtype=torch.int64, device=dev)
+    shard_bytes = torch.empty(world, dtype=torch.int64, device=dev)
+    _all_gather_flat(shard_bytes, mine, group)
+    max_shard = int(shard_bytes.max().item())
+    max_shard = (max_shard + 15) // 16 * 16
+    padded = torch.zeros(max_shard, dtype=torch.uint8, device=dev)
+    padded[:int(total_bytes)] = packed[:int(total_bytes)]
+    shards = torch.empty(world * max_shard, dtype=torch.uint8, device=dev)
+    _all_gather_flat(shards, padded, group)
+    return all_sizes, shards.view(world, max_shard), shard_bytes
