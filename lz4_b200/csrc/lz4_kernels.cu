@@ -78,8 +78,30 @@ __device__ __forceinline__ bool read_runlength(const uint8_t* src, int64_t& ip, 
     return true;
 }
 
-__device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut)
+/* Checkpoint = where the first token at or after input byte 256*j starts: (token position, output
+ * position, sequence index).  The expand kernel's lanes restart the token walk from these. */
+struct __align__(8) Checkpoint { uint16_t tok, op, seq, pad; };
+constexpr int kCkStride = 256;
+constexpr int kCkSlots = 256;                  // enough for inputs <= 65535 bytes
+constexpr uint16_t kCkEmpty = 0xFFFF;
+
+#define CK_VISIT()                                                                              \
+    do {                                                                                        \
+        if (ck && (ip >> 8) >= nextSlot) {                                                      \
+            const int64_t slot = ip >> 8;                                                       \
+            Checkpoint c; c.tok = kCkEmpty; c.op = 0; c.seq = 0; c.pad = 0;                     \
+            while (nextSlot < slot && nextSlot < kCkSlots) ck[nextSlot++] = c;                  \
+            if (slot < kCkSlots && op < 65536 && nseq < 65536) {                                \
+                c.tok = (uint16_t)ip; c.op = (uint16_t)op; c.seq = (uint16_t)nseq;              \
+                ck[slot] = c;                                                                   \
+            }                                                                                   \
+            nextSlot = slot + 1;                                                                \
+        }                                                                                       \
+    } while (0)
+
+__device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut, Checkpoint* ck)
 {
+    int64_t nextSlot = 0;
     int64_t n = nIn, cap = capIn, ip = 0, op = 0, ll = 0, ml = 0, add = 0;
     uint32_t token = 0, offset = 0, nseq = 0;
     bool fast;
@@ -90,6 +112,7 @@ __device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, u
     fast = (cap >= 64);                                                // lz4.c:2076
 
     for (;;) {
+        CK_VISIT();
         token = ldb(src + ip); ip++;
         ll = token >> 4;
         ml = token & 15;
@@ -131,6 +154,11 @@ safe_literals:
             if (ip + ll != n || op + ll > cap) goto bad;               // lz4.c:2312
             op += ll; nseq++;
             *nSeqOut = nseq;
+            if (ck) {                                                  // slots no token starts in
+                Checkpoint c; c.tok = kCkEmpty; c.op = 0; c.seq = 0; c.pad = 0;
+                const int64_t lastSlot = (n - 1) >> 8;
+                while (nextSlot <= lastSlot && nextSlot < kCkSlots) ck[nextSlot++] = c;
+            }
             return (int)op;                                            // lz4.c:2439
         }
         ip += ll; op += ll;
@@ -151,16 +179,43 @@ bad:
     return (int)(-ip) - 1;                                             // lz4.c:2443
 }
 
-__global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a, uint32_t* __restrict__ nSeq)
+/* workspace layout (lz4k_decode_workspace_bytes): header | nSeq[N] | fastList[N] | slowList[N] | ckpts[N][256] */
+struct WsHeader { uint32_t fastCount, slowCount, fastCursor, pad; };
+constexpr int kMaxSeqFast = 8192;
+
+struct WsView {
+    WsHeader* hdr; uint32_t* nSeq; uint32_t* fastList; uint32_t* slowList; Checkpoint* ck;
+};
+__host__ __device__ inline WsView ws_view(void* ws, int64_t n)
+{
+    WsView v;
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+    v.hdr = reinterpret_cast<WsHeader*>(p); p += 256;
+    v.nSeq = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
+    v.fastList = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
+    v.slowList = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
+    v.ck = reinterpret_cast<Checkpoint*>(p);
+    return v;
+}
+
+__global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
 {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.nBlocks) return;
+    WsView w = ws_view(a.workspace, a.nBlocks);
     const uint8_t* src = a.src + a.srcOff[b];
+    const int n = a.srcSize[b];
     int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
     uint32_t ns = 0;
-    int r = scan_block(src, a.srcSize[b], cap, &ns);
+    /* the smem expand kernel takes blocks whose input and output fit its 64 KB windows */
+    const bool maybeFast = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536);
+    int r = scan_block(src, n, cap, &ns, maybeFast ? (w.ck + b * kCkSlots) : nullptr);
     a.outSize[b] = r;
-    nSeq[b] = ns;
+    w.nSeq[b] = ns;
+    if (r > 0) {
+        if (maybeFast && ns <= kMaxSeqFast) w.fastList[atomicAdd(&w.hdr->fastCount, 1u)] = (uint32_t)b;
+        else w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
+    }
 }
 
 /* =============================================================================================
@@ -169,10 +224,10 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a, uint3
 __global__ void __launch_bounds__(128) lz4_expand_generic_kernel(lz4k_decode_args a)
 {
     const int lane = threadIdx.x & 31;
-    int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= a.nBlocks) return;
-    const int total = a.outSize[b];
-    if (total <= 0) return;                       // rejected (or empty) block: nothing to write
+    const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const WsView w = ws_view(a.workspace, a.nBlocks);
+    if (idx >= (int64_t)w.hdr->slowCount) return; // only blocks the scan accepted and left to this kernel
+    const int64_t b = w.slowList[idx];
     const uint8_t* __restrict__ src = a.src + a.srcOff[b];
     uint8_t* dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
     const int64_t n = a.srcSize[b];
@@ -201,6 +256,298 @@ __global__ void __launch_bounds__(128) lz4_expand_generic_kernel(lz4k_decode_arg
         }
         op += ml;
     }
+}
+
+/* =============================================================================================
+ * expand (fast): one CTA per 64 KB block, everything staged in shared memory
+ *
+ *   TMA bulk load  : compressed block  HBM -> smem            (cp.async.bulk + mbarrier)
+ *   phase A        : one LANE per 256-byte input slot restarts the token walk at the scan's
+ *                    checkpoint and writes an 8-byte record per sequence + a start-bit per
+ *                    sequence (bit index = output position)
+ *   rank           : exclusive scan of the popcounts of the start bits (sequence index of a byte =
+ *                    rank of the last start bit at or before it)
+ *   phase B        : one warp per 128-byte strip of output, one aligned 4-byte word per lane: the
+ *                    word is assembled from at most four sources (literals/match of the sequence
+ *                    covering its first byte and of the next one) read unaligned from smem, and
+ *                    stored once.  Match sources that are not final yet are waited for (strip
+ *                    frontier across warps, lane frontier inside the strip).
+ *   TMA bulk store : decoded block  smem -> HBM              (cp.async.bulk.global.shared::cta)
+ * HBM traffic is exactly the algorithmic bytes (C_i in, U_i out) plus the checkpoints.
+ * ============================================================================================= */
+constexpr int kFastThreads = 1024;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kInBytes = 65536 + 64;
+
+struct FastSmem {
+    alignas(16) uint8_t in[kInBytes];
+    alignas(16) uint8_t outPad[16];                 // reads of out[-4..-1] land here
+    alignas(16) uint8_t out[65536 + 16];
+    alignas(8) uint2 rec[kMaxSeqFast + 2];          // {outStart | litSrc<<16, litLen | offset<<16}
+    uint32_t bits[2048];                            // bit p: a sequence starts at output byte p
+    uint16_t seqbase[2048];                         // number of starts before bits[i]
+    uint32_t warpSum[32];
+    alignas(8) uint64_t mbar;
+    uint32_t curIdx;
+    uint32_t wdone[512];                            // bit w of wdone[s]: word w of strip s is final
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_1d(void* smemDst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smemDst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smemSrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(smemSrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+/* unaligned 32-bit read from a 4-aligned shared array at byte index `idx` (>= -4) */
+__device__ __forceinline__ uint32_t lds32u(const uint8_t* base, int idx)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (idx & ~3));
+    return __funnelshift_r(w[0], w[1], (uint32_t)(idx & 3) * 8u);
+}
+__device__ __forceinline__ uint32_t lowmask(int nbytes) { return nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (nbytes * 8)) - 1u); }
+__device__ __forceinline__ int clamp04(int v) { return min(4, max(v, 0)); }
+
+__global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_decode_args a)
+{
+    extern __shared__ __align__(16) uint8_t smemRaw[];
+    FastSmem& S = *reinterpret_cast<FastSmem*>(smemRaw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const WsView w = ws_view(a.workspace, a.nBlocks);
+    const uint32_t fastCount = w.hdr->fastCount;
+    uint32_t parity = 0;
+    volatile uint32_t* vWdone = S.wdone;
+
+    if (tid == 0) mbar_init(&S.mbar, 1);
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) S.curIdx = atomicAdd(&w.hdr->fastCursor, 1u);
+        __syncthreads();
+        const uint32_t idx = S.curIdx;
+        if (idx >= fastCount) break;
+        const int64_t b = w.fastList[idx];
+        const uint8_t* src = a.src + a.srcOff[b];
+        const int n = a.srcSize[b];
+        const int total = a.outSize[b];
+        const int nseq = (int)w.nSeq[b];
+        uint8_t* dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
+        const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+        const uint32_t loadBytes = (uint32_t)((head + n + 15) & ~15);
+
+        if (tid == 0) {
+            mbar_expect_tx(&S.mbar, loadBytes);
+            for (uint32_t o = 0; o < loadBytes; o += 16384u)
+                tma_load_1d(S.in + o, src - head + o, min(16384u, loadBytes - o), &S.mbar);
+        }
+        for (int k = tid; k < 2048; k += kFastThreads) S.bits[k] = 0;
+        if (tid < 512) S.wdone[tid] = 0;
+        __syncthreads();
+        while (!mbar_try_wait(&S.mbar, parity)) { }
+        parity ^= 1;
+
+        /* ---- phase A: sequence records + start bits ---- */
+        const uint8_t* in = S.in + head;
+        {
+            const int nslots = (n + kCkStride - 1) / kCkStride;
+            if (tid < nslots) {
+                const Checkpoint c = w.ck[b * kCkSlots + tid];
+                if (c.tok != kCkEmpty) {
+                    int tok = c.tok, op = c.op, k = c.seq;
+                    const int limit = (tid + 1) * kCkStride;
+                    while (tok < limit) {
+                        const uint32_t t = in[tok];
+                        int p = tok + 1;
+                        int ll = (int)(t >> 4);
+                        if (ll == 15) { uint32_t x; do { x = in[p++]; ll += (int)x; } while (x == 255); }
+                        const int ls = p;
+                        p += ll;
+                        if (op < total) atomicOr(&S.bits[op >> 5], 1u << (op & 31));
+                        const bool last = (p >= n);
+                        uint32_t off = 0;
+                        int ml = 0;
+                        if (!last) {
+                            off = (uint32_t)in[p] | ((uint32_t)in[p + 1] << 8);
+                            p += 2;
+                            ml = (int)(t & 15);
+                            if (ml == 15) { uint32_t x; do { x = in[p++]; ml += (int)x; } while (x == 255); }
+                            ml += kMinMatch;
+                        }
+                        S.rec[k] = make_uint2((uint32_t)op | ((uint32_t)ls << 16), (uint32_t)ll | (off << 16));
+                        if (last) break;
+                        op += ll + ml; tok = p; k++;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        /* ---- rank: seqbase[i] = number of start bits in bits[0..i) ---- */
+        {
+            constexpr int WPT = 2048 / kFastThreads;
+            uint32_t cnt[WPT], x = 0;
+            #pragma unroll
+            for (int j = 0; j < WPT; j++) { cnt[j] = __popc(S.bits[tid * WPT + j]); x += cnt[j]; }
+            uint32_t incl = x;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += y; }
+            if (lane == 31) S.warpSum[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t v = (lane < kFastWarps) ? S.warpSum[lane] : 0;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, v, d); if (lane >= d) v += y; }
+                S.warpSum[lane] = v;
+            }
+            __syncthreads();
+            uint32_t ex = incl - x + (warp ? S.warpSum[warp - 1] : 0);
+            #pragma unroll
+            for (int j = 0; j < WPT; j++) { S.seqbase[tid * WPT + j] = (uint16_t)ex; ex += cnt[j]; }
+            if (tid == 0) tma_wait_read0();        // previous block's bulk store has finished reading S.out
+        }
+        __syncthreads();
+
+        /* ---- phase B: assemble the output, one aligned word per lane ---- */
+        const int nstrips = (total + 127) >> 7;
+        for (int s = warp; s < nstrips; s += kFastWarps) {
+            const int wb = s << 7;
+            const int p = wb + (lane << 2);
+            const bool active = p < total;
+            int oA = 0, lsA = 0, llA = 0, offA = 0, mA = 0, oB = 0, lsB = 0, llB = 0, offB = 0, mB = 0;
+            int nA = 4, nB = 4, nC = 4;
+            bool slow = false, needMA = false, needMB = false;
+            /* output words whose bytes this lane reads as match sources: [w0a..w1a], [w0b..w1b]
+             * (inclusive, -1 = none) */
+            int w0a = -1, w1a = -1, w0b = -1, w1b = -1;
+            uint32_t LA = 0, LB = 0;
+            if (active) {
+                const uint32_t bw = S.bits[p >> 5];
+                const int kA = (int)S.seqbase[p >> 5] + __popc(bw & ((2u << (p & 31)) - 1u)) - 1;
+                const uint2 rA = S.rec[kA];
+                oA = (int)(rA.x & 0xFFFF); lsA = (int)(rA.x >> 16); llA = (int)(rA.y & 0xFFFF); offA = (int)(rA.y >> 16);
+                mA = oA + llA;
+                nA = clamp04(mA - p);
+                if (kA + 1 < nseq) {
+                    const uint2 rB = S.rec[kA + 1];
+                    oB = (int)(rB.x & 0xFFFF); lsB = (int)(rB.x >> 16); llB = (int)(rB.y & 0xFFFF); offB = (int)(rB.y >> 16);
+                    if (oB == 0) oB = 65536;                   // only an empty final sequence can start at 65536
+                    mB = oB + llB;
+                    nB = clamp04(oB - p);
+                    nC = clamp04(mB - p);
+                }
+                needMA = (nB > nA) && offA != 0;               // offset 0 decodes to zero bytes (lz4.c:2407)
+                needMB = (nC < 4) && offB != 0;
+                if (needMA) {
+                    int sa, sb;                                // source bytes [sa, sb) of the output
+                    if (offA < 4) { slow = true; sa = mA - offA; sb = min(mA, p); }
+                    else { sa = p + nA - offA; sb = p + nB - offA; }
+                    if (sb > sa) { w0a = sa >> 2; w1a = (sb - 1) >> 2; }
+                }
+                if (needMB) {
+                    int sa, sb;
+                    if (offB < 4) { slow = true; sa = mB - offB; sb = min(mB, p); }
+                    else { sa = p + nC - offB; sb = p + 4 - offB; }
+                    if (sb > sa) { w0b = sa >> 2; w1b = (sb - 1) >> 2; }
+                }
+                if (nA > 0) LA = lds32u(S.in, head + lsA + (p - oA));
+                if (nC > nB) LB = lds32u(S.in, head + lsB + (p - oB));
+            }
+            bool done = !active;
+            unsigned published = 0;
+            for (;;) {
+                if (!done) {
+                    bool ready = true;
+                    if (w0a >= 0) ready = ((vWdone[w0a >> 5] >> (w0a & 31)) & (vWdone[w1a >> 5] >> (w1a & 31)) & 1u) != 0;
+                    if (ready && w0b >= 0) ready = ((vWdone[w0b >> 5] >> (w0b & 31)) & (vWdone[w1b >> 5] >> (w1b & 31)) & 1u) != 0;
+                    if (ready) {
+                        __threadfence_block();                 // flag reads before data reads
+                        uint32_t word;
+                        if (!slow) {
+                            uint32_t MA = 0, MB = 0;
+                            if (needMA) MA = lds32u(S.out, p - offA);
+                            if (needMB) MB = lds32u(S.out, p - offB);
+                            const uint32_t ka = lowmask(nA), kb = lowmask(nB), kc = lowmask(nC);
+                            word = (LA & ka) | (MA & kb & ~ka) | (LB & kc & ~kb) | (MB & ~kc);
+                        } else {
+                            /* general byte-serial path (periods 1..3 and anything sharing this word):
+                             * a match byte x reads m - off + ((x - m) mod off), always before the match */
+                            word = 0;
+                            #pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const int x = p + i;
+                                uint32_t v;
+                                if (x < mA) v = S.in[head + lsA + (x - oA)];
+                                else if (i < nC && i >= nB) v = S.in[head + lsB + (x - oB)];
+                                else {
+                                    const int m = (i < nB) ? mA : mB;
+                                    const int off = (i < nB) ? offA : offB;
+                                    if (off == 0) v = 0;
+                                    else {
+                                        int sidx = x - off;
+                                        if (sidx >= m) sidx = m - off + ((x - m) % off);
+                                        v = (sidx >= p) ? ((word >> (8 * (sidx - p))) & 0xFFu) : (uint32_t)S.out[sidx];
+                                    }
+                                }
+                                word |= v << (8 * i);
+                            }
+                        }
+                        *reinterpret_cast<uint32_t*>(S.out + p) = word;
+                        done = true;
+                    }
+                }
+                __syncwarp();
+                const unsigned dm = __ballot_sync(kFull, done);
+                if (dm != published) {                         // publish the words finished this round
+                    if (lane == 0) { __threadfence_block(); vWdone[s] = dm; }
+                    published = dm;
+                } else {
+                    __nanosleep(20);
+                }
+                if (dm == kFull) break;
+            }
+        }
+        __syncthreads();
+
+        /* ---- store: smem -> HBM ---- */
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            fence_proxy_async();
+            __syncthreads();
+            const uint32_t bulk = (uint32_t)total & ~15u;
+            if (tid == 0 && bulk) {
+                for (uint32_t o = 0; o < bulk; o += 16384u) tma_store_1d(dst + o, S.out + o, min(16384u, bulk - o));
+                tma_commit();
+            }
+            if (tid < (total & 15)) dst[bulk + tid] = S.out[bulk + tid];
+        } else {
+            for (int k = tid; k < total; k += kFastThreads) dst[k] = S.out[k];
+        }
+    }
+    if (tid == 0) tma_wait_all0();
 }
 
 /* =============================================================================================
@@ -506,24 +853,39 @@ uint64_t lz4k_launch_count(void) { return g_launches; }
 size_t lz4k_decode_workspace_bytes(int64_t nBlocks)
 {
     if (nBlocks < 0) return 0;
-    return (size_t)nBlocks * sizeof(uint32_t) + 256;
+    const size_t lst = (((size_t)nBlocks * 4 + 255) / 256) * 256;
+    return 256 + 3 * lst + (size_t)nBlocks * kCkSlots * sizeof(Checkpoint) + 256;
 }
 
 int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (a->nBlocks == 0) return 0;
-    uint32_t* nSeq = reinterpret_cast<uint32_t*>(a->workspace);
+    {   /* opt in to the 205 KB of dynamic shared memory (per device, cheap to repeat) */
+        cudaError_t e = cudaFuncSetAttribute(lz4_expand_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+        if (e != cudaSuccess) return (int)e;
+    }
     if (phases & 1) {
+        cudaError_t e = cudaMemsetAsync(a->workspace, 0, 256, s);     // WsHeader: list counters
+        if (e != cudaSuccess) return (int)e;
         const int threads = 128;
         const int64_t grid = (a->nBlocks + threads - 1) / threads;
-        lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a, nSeq);
+        lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
         g_launches++;
     }
     if (phases & 2) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        WsView w = ws_view(a->workspace, a->nBlocks);
+        cudaError_t e = cudaMemsetAsync(&w.hdr->fastCursor, 0, sizeof(uint32_t), s);
+        if (e != cudaSuccess) return (int)e;
+        int64_t grid = a->nBlocks < sms ? a->nBlocks : sms;          // persistent: one CTA per SM
+        lz4_expand_fast_kernel<<<(unsigned)grid, kFastThreads, sizeof(FastSmem), s>>>(*a);
+        g_launches++;
         const int threads = 128;   // 4 warps = 4 blocks per CTA
-        const int64_t grid = (a->nBlocks * 32 + threads - 1) / threads;
-        lz4_expand_generic_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
+        const int64_t grid2 = (a->nBlocks * 32 + threads - 1) / threads;
+        lz4_expand_generic_kernel<<<(unsigned)grid2, threads, 0, s>>>(*a);
         g_launches++;
     }
     return (int)cudaGetLastError();
