@@ -283,7 +283,7 @@ struct FastSmem {
     alignas(16) uint8_t in[kInBytes];
     alignas(16) uint8_t outPad[16];                 // reads of out[-4..-1] land here
     alignas(16) uint8_t out[65536 + 16];
-    alignas(8) uint2 rec[kMaxSeqFast + 2];          // {outStart | litSrc<<16, litLen | offset<<16}
+    alignas(8) uint2 rec[kMaxSeqFast + 2];          // {matchStart | nextStart<<16, litDelta | offset<<16}
     uint32_t bits[2048];                            // bit p: a sequence starts at output byte p
     uint16_t seqbase[2048];                         // number of starts before bits[i]
     uint32_t warpSum[32];
@@ -332,6 +332,38 @@ __device__ __forceinline__ uint32_t lds32u(const uint8_t* base, int idx)
 }
 __device__ __forceinline__ uint32_t lowmask(int nbytes) { return nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (nbytes * 8)) - 1u); }
 __device__ __forceinline__ int clamp04(int v) { return min(4, max(v, 0)); }
+
+/* shl.b32 clamps shift amounts >= 32 to a zero result (C's << does not) */
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, int sh)
+{
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));
+    return r;
+}
+
+/* Rare path of phase B: builds the match bytes of one output word byte by byte.  `word` holds the
+ * literal bytes already.  A match byte at x with offset off and match start m reads x - off, or,
+ * when that is inside the match itself (period < 4), m - off + ((x - m) mod off) -- always before
+ * the match start.  Sources inside this very word come from the bytes assembled so far. */
+__device__ __noinline__ uint32_t assemble_bytewise(const uint8_t* in, const uint8_t* out, int p, uint32_t word,
+                                                    int nA, int nB, int nC, int mA, int offA, int mB, int offB)
+{
+    (void)in;
+    for (int i = nA; i < 4; i++) {
+        if (i >= nB && i < nC) continue;                       // literal of the next sequence: already in place
+        const int m = (i < nB) ? mA : mB;
+        const int off = (i < nB) ? offA : offB;
+        const int x = p + i;
+        uint32_t v = 0;
+        if (off != 0) {
+            int sidx = x - off;
+            if (sidx >= m) sidx = m - off + ((x - m) % off);
+            v = (sidx >= p) ? ((word >> (8 * (sidx - p))) & 0xFFu) : (uint32_t)out[sidx];
+        }
+        word = (word & ~(0xFFu << (8 * i))) | (v << (8 * i));
+    }
+    return word;
+}
 
 __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_decode_args a)
 {
@@ -398,7 +430,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                             if (ml == 15) { uint32_t x; do { x = in[p++]; ml += (int)x; } while (x == 255); }
                             ml += kMinMatch;
                         }
-                        S.rec[k] = make_uint2((uint32_t)op | ((uint32_t)ls << 16), (uint32_t)ll | (off << 16));
+                        {   /* record: {matchStart | nextStart<<16, (litSrc-outStart)&0xFFFF | offset<<16} */
+                            const uint32_t mstart = (uint32_t)(op + ll);
+                            const uint32_t nxt = last ? (uint32_t)total : (uint32_t)(op + ll + ml);
+                            S.rec[k] = make_uint2((mstart & 0xFFFFu) | (nxt << 16), ((uint32_t)(ls - op) & 0xFFFFu) | (off << 16));
+                        }
                         if (last) break;
                         op += ll + ml; tok = p; k++;
                     }
@@ -435,100 +471,104 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
         /* ---- phase B: assemble the output, one aligned word per lane ---- */
         const int nstrips = (total + 127) >> 7;
         for (int s = warp; s < nstrips; s += kFastWarps) {
-            const int wb = s << 7;
-            const int p = wb + (lane << 2);
+            const int p = (s << 7) + (lane << 2);
             const bool active = p < total;
-            int oA = 0, lsA = 0, llA = 0, offA = 0, mA = 0, oB = 0, lsB = 0, llB = 0, offB = 0, mB = 0;
-            int nA = 4, nB = 4, nC = 4;
-            bool slow = false, needMA = false, needMB = false;
-            /* output words whose bytes this lane reads as match sources: [w0a..w1a], [w0b..w1b]
-             * (inclusive, -1 = none) */
-            int w0a = -1, w1a = -1, w0b = -1, w1b = -1;
-            uint32_t LA = 0, LB = 0;
+            uint32_t word = 0;
+            bool done = !active;
+            /* sequence A covers byte p; B = the next one (only consulted when it starts inside this word) */
+            int mA = 0, eA = 0, offA = 0, mB = 0, offB = 0, nA = 4, nB = 4, nC = 4;
+            uint32_t dA = 0, dB = 0;
+            bool needMA = false, needMB = false, slow = false;
+            int w0a = -1, w1a = -1, w0b = -1, w1b = -1;       // output words read as match sources
             if (active) {
                 const uint32_t bw = S.bits[p >> 5];
-                const int kA = (int)S.seqbase[p >> 5] + __popc(bw & ((2u << (p & 31)) - 1u)) - 1;
+                const int kA = (int)S.seqbase[p >> 5] + __popc(bw & (0xFFFFFFFFu >> (31 - (p & 31)))) - 1;
                 const uint2 rA = S.rec[kA];
-                oA = (int)(rA.x & 0xFFFF); lsA = (int)(rA.x >> 16); llA = (int)(rA.y & 0xFFFF); offA = (int)(rA.y >> 16);
-                mA = oA + llA;
+                mA = (int)(rA.x & 0xFFFFu);
+                eA = (int)(rA.x >> 16);
+                dA = rA.y & 0xFFFFu;
+                offA = (int)(rA.y >> 16);
+                /* 16-bit wrap: a match start / next start of 65536 is stored as 0 */
+                if (mA == 0 && kA != 0) mA = 65536;
+                if (eA == 0) eA = 65536;
                 nA = clamp04(mA - p);
-                if (kA + 1 < nseq) {
+                nB = clamp04(eA - p);
+                if (nB < 4 && kA + 1 < nseq) {
                     const uint2 rB = S.rec[kA + 1];
-                    oB = (int)(rB.x & 0xFFFF); lsB = (int)(rB.x >> 16); llB = (int)(rB.y & 0xFFFF); offB = (int)(rB.y >> 16);
-                    if (oB == 0) oB = 65536;                   // only an empty final sequence can start at 65536
-                    mB = oB + llB;
-                    nB = clamp04(oB - p);
+                    mB = (int)(rB.x & 0xFFFFu);
+                    if (mB == 0) mB = 65536;
+                    dB = rB.y & 0xFFFFu;
+                    offB = (int)(rB.y >> 16);
                     nC = clamp04(mB - p);
+                } else {
+                    nC = nB;                                   // no further sequence inside this word
                 }
                 needMA = (nB > nA) && offA != 0;               // offset 0 decodes to zero bytes (lz4.c:2407)
-                needMB = (nC < 4) && offB != 0;
-                if (needMA) {
-                    int sa, sb;                                // source bytes [sa, sb) of the output
-                    if (offA < 4) { slow = true; sa = mA - offA; sb = min(mA, p); }
-                    else { sa = p + nA - offA; sb = p + nB - offA; }
-                    if (sb > sa) { w0a = sa >> 2; w1a = (sb - 1) >> 2; }
+                needMB = (nC < 4) && offB != 0 && (nB < 4);
+                uint32_t LA = 0, LB = 0;
+                if (nA > 0) LA = lds32u(S.in, head + (int)((p + dA) & 0xFFFFu));
+                if (nC > nB) LB = lds32u(S.in, head + (int)((p + dB) & 0xFFFFu));
+                const uint32_t sA = shl_clamp(0xFFFFFFFFu, nA * 8), sB = shl_clamp(0xFFFFFFFFu, nB * 8);
+                word = (LA & ~sA) | (LB & sB);                 // literal bytes; match bytes are merged below
+                /* exact source words of the match pieces (periods < 4 take the careful path) */
+                slow = (needMA && offA < 4) || (needMB && offB < 4);
+                if (needMA) { w0a = (p + nA - offA) >> 2; w1a = (p + nB - offA - 1) >> 2; }
+                if (needMB) { w0b = (p + nC - offB) >> 2; w1b = (p + 3 - offB) >> 2; }
+                bool ready = !slow;
+                if (needMA) ready = ready && (((vWdone[w0a >> 5] >> (w0a & 31)) & (vWdone[w1a >> 5] >> (w1a & 31)) & 1u) != 0);
+                if (needMB) ready = ready && (((vWdone[w0b >> 5] >> (w0b & 31)) & (vWdone[w1b >> 5] >> (w1b & 31)) & 1u) != 0);
+                if (ready) {
+                    __threadfence_block();
+                    uint32_t MA = 0, MB = 0;
+                    if (needMA) MA = lds32u(S.out, p - offA);
+                    if (needMB) MB = lds32u(S.out, p - offB);
+                    const uint32_t sC = shl_clamp(0xFFFFFFFFu, nC * 8);
+                    word = (word & (~sA | (sB & ~sC))) | (MA & sA & ~sB) | (MB & sC);
+                    *reinterpret_cast<uint32_t*>(S.out + p) = word;
+                    done = true;
                 }
-                if (needMB) {
-                    int sa, sb;
-                    if (offB < 4) { slow = true; sa = mB - offB; sb = min(mB, p); }
-                    else { sa = p + nC - offB; sb = p + 4 - offB; }
-                    if (sb > sa) { w0b = sa >> 2; w1b = (sb - 1) >> 2; }
-                }
-                if (nA > 0) LA = lds32u(S.in, head + lsA + (p - oA));
-                if (nC > nB) LB = lds32u(S.in, head + lsB + (p - oB));
             }
-            bool done = !active;
-            unsigned published = 0;
-            for (;;) {
-                if (!done) {
-                    bool ready = true;
-                    if (w0a >= 0) ready = ((vWdone[w0a >> 5] >> (w0a & 31)) & (vWdone[w1a >> 5] >> (w1a & 31)) & 1u) != 0;
-                    if (ready && w0b >= 0) ready = ((vWdone[w0b >> 5] >> (w0b & 31)) & (vWdone[w1b >> 5] >> (w1b & 31)) & 1u) != 0;
-                    if (ready) {
-                        __threadfence_block();                 // flag reads before data reads
-                        uint32_t word;
-                        if (!slow) {
-                            uint32_t MA = 0, MB = 0;
-                            if (needMA) MA = lds32u(S.out, p - offA);
-                            if (needMB) MB = lds32u(S.out, p - offB);
-                            const uint32_t ka = lowmask(nA), kb = lowmask(nB), kc = lowmask(nC);
-                            word = (LA & ka) | (MA & kb & ~ka) | (LB & kc & ~kb) | (MB & ~kc);
-                        } else {
-                            /* general byte-serial path (periods 1..3 and anything sharing this word):
-                             * a match byte x reads m - off + ((x - m) mod off), always before the match */
-                            word = 0;
-                            #pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                const int x = p + i;
-                                uint32_t v;
-                                if (x < mA) v = S.in[head + lsA + (x - oA)];
-                                else if (i < nC && i >= nB) v = S.in[head + lsB + (x - oB)];
-                                else {
-                                    const int m = (i < nB) ? mA : mB;
-                                    const int off = (i < nB) ? offA : offB;
-                                    if (off == 0) v = 0;
-                                    else {
-                                        int sidx = x - off;
-                                        if (sidx >= m) sidx = m - off + ((x - m) % off);
-                                        v = (sidx >= p) ? ((word >> (8 * (sidx - p))) & 0xFFu) : (uint32_t)S.out[sidx];
-                                    }
-                                }
-                                word |= v << (8 * i);
+            __syncwarp();
+            unsigned dm = __ballot_sync(kFull, done);
+            if (lane == 0) { __threadfence_block(); vWdone[s] = dm; }
+            if (dm != kFull) {
+                /* careful path: poll the word-level flags of the exact source words; periods < 4 and
+                 * in-word dependencies go through the byte-serial routine */
+                if (!done && slow) {                           // sources of a period-<4 piece: [m - off, min(m, p))
+                    if (needMA && offA < 4) { const int sa = mA - offA, sb = min(mA, p); w0a = (sb > sa) ? (sa >> 2) : -1; w1a = (sb - 1) >> 2; }
+                    if (needMB && offB < 4) { const int sa = mB - offB, sb = min(mB, p); w0b = (sb > sa) ? (sa >> 2) : -1; w1b = (sb - 1) >> 2; }
+                }
+                for (;;) {
+                    if (!done) {
+                        bool ready = true;
+                        if (w0a >= 0) ready = ((vWdone[w0a >> 5] >> (w0a & 31)) & (vWdone[w1a >> 5] >> (w1a & 31)) & 1u) != 0;
+                        if (ready && w0b >= 0) ready = ((vWdone[w0b >> 5] >> (w0b & 31)) & (vWdone[w1b >> 5] >> (w1b & 31)) & 1u) != 0;
+                        if (ready) {
+                            __threadfence_block();             // flag reads before data reads
+                            if (!slow) {
+                                uint32_t MA = 0, MB = 0;
+                                if (needMA) MA = lds32u(S.out, p - offA);
+                                if (needMB) MB = lds32u(S.out, p - offB);
+                                const uint32_t sA = shl_clamp(0xFFFFFFFFu, nA * 8), sB = shl_clamp(0xFFFFFFFFu, nB * 8);
+                                const uint32_t sC = shl_clamp(0xFFFFFFFFu, nC * 8);
+                                word = (word & (~sA | (sB & ~sC))) | (MA & sA & ~sB) | (MB & sC);
+                            } else {
+                                word = assemble_bytewise(S.in + head, S.out, p, word, nA, nB, nC, mA, offA, mB, offB);
                             }
+                            *reinterpret_cast<uint32_t*>(S.out + p) = word;
+                            done = true;
                         }
-                        *reinterpret_cast<uint32_t*>(S.out + p) = word;
-                        done = true;
                     }
+                    __syncwarp();
+                    const unsigned dm2 = __ballot_sync(kFull, done);
+                    if (dm2 != dm) {                           // publish the words finished this round
+                        if (lane == 0) { __threadfence_block(); vWdone[s] = dm2; }
+                        dm = dm2;
+                    } else {
+                        __nanosleep(20);
+                    }
+                    if (dm == kFull) break;
                 }
-                __syncwarp();
-                const unsigned dm = __ballot_sync(kFull, done);
-                if (dm != published) {                         // publish the words finished this round
-                    if (lane == 0) { __threadfence_block(); vWdone[s] = dm; }
-                    published = dm;
-                } else {
-                    __nanosleep(20);
-                }
-                if (dm == kFull) break;
             }
         }
         __syncthreads();
