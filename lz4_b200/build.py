@@ -19,7 +19,9 @@ SOURCES = ["lz4_kernels.cu", "lz4_api.c"]
 HEADERS = [os.path.join(CSRC, "lz4_kernels.h"), os.path.join(ROOT, "include", "lz4_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math", "-diag-suppress", "177"]
+if os.environ.get("LZ4K_PHASE_TIMING"):          # developer build: per-phase clock64 counters
+    NVCC_FLAGS.append("-DLZ4K_PHASE_TIMING")
 CC_FLAGS = ["-O2", "-fPIC", "-std=c99", "-Wall", "-Wextra", "-fvisibility=hidden",
             "-I" + os.path.join(CUDA_HOME, "include")]
 

@@ -31,6 +31,14 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 unsigned long long g_launches = 0;
 
+/* optional phase timing of the fast expand kernel (thread 0 of each CTA; enabled with -DLZ4K_PHASE_TIMING) */
+__device__ unsigned long long g_phaseCycles[8];
+#ifdef LZ4K_PHASE_TIMING
+#define PHASE_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); atomicAdd(&g_phaseCycles[i], (unsigned long long)(t_ - tPhase)); tPhase = t_; } } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return __ldg(p); }
 __device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return __ldg(p) | (__ldg(p + 1) << 8); }
 
@@ -280,6 +288,7 @@ constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kInBytes = 65536 + 64;
 
 struct FastSmem {
+    alignas(16) uint8_t inPad[16];                  // reads of in[-8..-1] land here
     alignas(16) uint8_t in[kInBytes];
     alignas(16) uint8_t outPad[16];                 // reads of out[-4..-1] land here
     alignas(16) uint8_t out[65536 + 16];
@@ -289,7 +298,7 @@ struct FastSmem {
     uint32_t warpSum[32];
     alignas(8) uint64_t mbar;
     uint32_t curIdx;
-    uint32_t wdone[512];                            // bit w of wdone[s]: word w of strip s is final
+    alignas(16) uint8_t done8[8192];                // done8[c] != 0: output bytes [8c, 8c+8) are final
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -324,14 +333,18 @@ __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-/* unaligned 32-bit read from a 4-aligned shared array at byte index `idx` (>= -4) */
-__device__ __forceinline__ uint32_t lds32u(const uint8_t* base, int idx)
+
+
+/* unaligned 64-bit read from a 4-aligned shared array at byte index `idx` (>= -4) */
+__device__ __forceinline__ uint64_t lds64u(const uint8_t* base, int idx)
 {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (idx & ~3));
-    return __funnelshift_r(w[0], w[1], (uint32_t)(idx & 3) * 8u);
+    const uint32_t sh = (uint32_t)(idx & 3) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
 }
-__device__ __forceinline__ uint32_t lowmask(int nbytes) { return nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (nbytes * 8)) - 1u); }
-__device__ __forceinline__ int clamp04(int v) { return min(4, max(v, 0)); }
+
+__device__ __forceinline__ int clamp08(int v) { return min(8, max(v, 0)); }
 
 /* shl.b32 clamps shift amounts >= 32 to a zero result (C's << does not) */
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, int sh)
@@ -340,29 +353,56 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, int sh)
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));
     return r;
 }
-
-/* Rare path of phase B: builds the match bytes of one output word byte by byte.  `word` holds the
- * literal bytes already.  A match byte at x with offset off and match start m reads x - off, or,
- * when that is inside the match itself (period < 4), m - off + ((x - m) mod off) -- always before
- * the match start.  Sources inside this very word come from the bytes assembled so far. */
-__device__ __noinline__ uint32_t assemble_bytewise(const uint8_t* in, const uint8_t* out, int p, uint32_t word,
-                                                    int nA, int nB, int nC, int mA, int offA, int mB, int offB)
+/* 64-bit mask of the low b bytes, b in [0, 8] */
+__device__ __forceinline__ uint64_t lowbytes(int b)
 {
-    (void)in;
-    for (int i = nA; i < 4; i++) {
-        if (i >= nB && i < nC) continue;                       // literal of the next sequence: already in place
-        const int m = (i < nB) ? mA : mB;
-        const int off = (i < nB) ? offA : offB;
+    const uint32_t lo = ~shl_clamp(0xFFFFFFFFu, 8 * b);
+    const uint32_t hi = ~shl_clamp(0xFFFFFFFFu, max(8 * b - 32, 0));
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+/* Are output bytes [lo, hi] (hi - lo < 8, both below the caller's chunk) final?  Chunks that belong
+ * to other warps are waited for; chunks of the caller's own strip only polled (see phase B). */
+__device__ __forceinline__ bool sources_ready(const volatile uint8_t* done8, int lo, int hi, int ownChunk0)
+{
+    const int c0 = lo >> 3, c1 = hi >> 3;
+    if (c1 >= ownChunk0) return (done8[c0] & done8[c1]) != 0;
+    while (!(done8[c0] & done8[c1])) { }
+    return true;
+}
+
+/* Rare path of phase B: the match bytes of one chunk built one at a time, for pieces whose period
+ * is < 8.  Byte x of a match starting at m with offset off reads x - off, or -- when that is inside
+ * the match itself -- m - off + ((x - m) mod off), which is always before the match start.  Sources
+ * inside this chunk (>= p) come from the bytes assembled so far. */
+__device__ __noinline__ uint64_t match_bytes_serial(const uint8_t* out, const volatile uint8_t* done8, int p, int ownChunk0,
+                                                     uint64_t lit, int b1, int b2, int b3, int b4, int b5,
+                                                     int mA, int mB, int mC, int offA, int offB, int offC,
+                                                     bool needA, bool needB, bool needC, bool& blocked)
+{
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++) {
+        int m, off;
+        if (i >= b1 && i < b2) { if (!needA) continue; m = mA; off = offA; }
+        else if (i >= b3 && i < b4) { if (!needB) continue; m = mB; off = offB; }
+        else if (i >= b5) { if (!needC) continue; m = mC; off = offC; }
+        else continue;                                         // literal byte
         const int x = p + i;
-        uint32_t v = 0;
-        if (off != 0) {
-            int sidx = x - off;
-            if (sidx >= m) sidx = m - off + ((x - m) % off);
-            v = (sidx >= p) ? ((word >> (8 * (sidx - p))) & 0xFFu) : (uint32_t)out[sidx];
+        int sidx = x - off;
+        if (sidx >= m) sidx = m - off + ((x - m) % off);
+        uint32_t byte;
+        if (sidx >= p) {
+            byte = (uint32_t)(((lit | v) >> (8 * (sidx - p))) & 0xFFu);
+        } else {
+            const int c = sidx >> 3;
+            if (c >= ownChunk0) { if (!done8[c]) { blocked = true; return 0; } }
+            else { while (!done8[c]) { } }
+            __threadfence_block();
+            byte = out[sidx];
         }
-        word = (word & ~(0xFFu << (8 * i))) | (v << (8 * i));
+        v |= (uint64_t)byte << (8 * i);
     }
-    return word;
+    return v;
 }
 
 __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_decode_args a)
@@ -373,10 +413,13 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
     const WsView w = ws_view(a.workspace, a.nBlocks);
     const uint32_t fastCount = w.hdr->fastCount;
     uint32_t parity = 0;
-    volatile uint32_t* vWdone = S.wdone;
+    volatile uint8_t* vDone8 = S.done8;
 
     if (tid == 0) mbar_init(&S.mbar, 1);
     __syncthreads();
+#ifdef LZ4K_PHASE_TIMING
+    long long tPhase = clock64();
+#endif
 
     for (;;) {
         if (tid == 0) S.curIdx = atomicAdd(&w.hdr->fastCursor, 1u);
@@ -398,10 +441,12 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                 tma_load_1d(S.in + o, src - head + o, min(16384u, loadBytes - o), &S.mbar);
         }
         for (int k = tid; k < 2048; k += kFastThreads) S.bits[k] = 0;
-        if (tid < 512) S.wdone[tid] = 0;
+        reinterpret_cast<uint64_t*>(S.done8)[tid] = 0;          // kFastThreads * 8 == 8192
         __syncthreads();
+        PHASE_MARK(0);                                     // fetch + zeroing
         while (!mbar_try_wait(&S.mbar, parity)) { }
         parity ^= 1;
+        PHASE_MARK(1);                                     // TMA load wait
 
         /* ---- phase A: sequence records + start bits ---- */
         const uint8_t* in = S.in + head;
@@ -442,6 +487,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
             }
         }
         __syncthreads();
+        PHASE_MARK(2);                                     // phase A
 
         /* ---- rank: seqbase[i] = number of start bits in bits[0..i) ---- */
         {
@@ -464,111 +510,92 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
             uint32_t ex = incl - x + (warp ? S.warpSum[warp - 1] : 0);
             #pragma unroll
             for (int j = 0; j < WPT; j++) { S.seqbase[tid * WPT + j] = (uint16_t)ex; ex += cnt[j]; }
+            PHASE_MARK(3);                                 // rank
             if (tid == 0) tma_wait_read0();        // previous block's bulk store has finished reading S.out
+            PHASE_MARK(4);                                 // wait for previous store
         }
         __syncthreads();
 
-        /* ---- phase B: assemble the output, one aligned word per lane ---- */
-        const int nstrips = (total + 127) >> 7;
+        /* ---- phase B: assemble the output, one aligned 8-byte chunk per lane ----
+         * An 8-byte chunk intersects at most three sequences (every sequence but the last is >= 4
+         * bytes long): A covers its first byte, then B, then C -- hence at most six pieces
+         * A.lit A.match B.lit B.match C.lit C.match with boundaries b1..b5 (bytes from the chunk
+         * start).  The source of output byte q is in[q + delta] for literals and out[q - offset] for
+         * matches, so each piece is ONE unaligned 8-byte load at the chunk's own position and a byte
+         * mask -- no loop, no shifting.  A match piece needs the done-flags of the (at most two)
+         * chunks holding its source bytes: chunks of other warps are waited for in place; chunks of
+         * this warp's own strip (lower lanes) cannot be spun on inside divergent code, so the lane
+         * parks and retries after the warp has reconverged. */
+        const int nstrips = (total + 255) >> 8;
         for (int s = warp; s < nstrips; s += kFastWarps) {
-            const int p = (s << 7) + (lane << 2);
-            const bool active = p < total;
-            uint32_t word = 0;
-            bool done = !active;
-            /* sequence A covers byte p; B = the next one (only consulted when it starts inside this word) */
-            int mA = 0, eA = 0, offA = 0, mB = 0, offB = 0, nA = 4, nB = 4, nC = 4;
-            uint32_t dA = 0, dB = 0;
-            bool needMA = false, needMB = false, slow = false;
-            int w0a = -1, w1a = -1, w0b = -1, w1b = -1;       // output words read as match sources
-            if (active) {
+            const int p = (s << 8) + (lane << 3);
+            const int ownChunk0 = s << 5;                      // first chunk of this warp's strip
+            bool pending = p < total;
+            uint64_t acc = 0;
+            int b1 = 8, b2 = 8, b3 = 8, b4 = 8, b5 = 8;
+            int mA = 0, mB = 0, mC = 0, offA = 0, offB = 0, offC = 0;
+            bool needA = false, needB = false, needC = false, anyShort = false;
+            if (pending) {
                 const uint32_t bw = S.bits[p >> 5];
                 const int kA = (int)S.seqbase[p >> 5] + __popc(bw & (0xFFFFFFFFu >> (31 - (p & 31)))) - 1;
-                const uint2 rA = S.rec[kA];
-                mA = (int)(rA.x & 0xFFFFu);
-                eA = (int)(rA.x >> 16);
-                dA = rA.y & 0xFFFFu;
-                offA = (int)(rA.y >> 16);
-                /* 16-bit wrap: a match start / next start of 65536 is stored as 0 */
-                if (mA == 0 && kA != 0) mA = 65536;
-                if (eA == 0) eA = 65536;
-                nA = clamp04(mA - p);
-                nB = clamp04(eA - p);
-                if (nB < 4 && kA + 1 < nseq) {
-                    const uint2 rB = S.rec[kA + 1];
-                    mB = (int)(rB.x & 0xFFFFu);
-                    if (mB == 0) mB = 65536;
-                    dB = rB.y & 0xFFFFu;
-                    offB = (int)(rB.y >> 16);
-                    nC = clamp04(mB - p);
-                } else {
-                    nC = nB;                                   // no further sequence inside this word
+                const uint2 rA = S.rec[kA], rB = S.rec[kA + 1], rC = S.rec[kA + 2];
+                const bool vB = kA + 1 < nseq, vC = kA + 2 < nseq;
+                mA = (int)(rA.x & 0xFFFFu); if (mA == 0 && kA != 0) mA = 65536;      // 16-bit wrap of 65536
+                int eA = (int)(rA.x >> 16); if (eA == 0) eA = 65536;
+                mB = (int)(rB.x & 0xFFFFu); if (mB == 0) mB = 65536;
+                int eB = (int)(rB.x >> 16); if (eB == 0) eB = 65536;
+                mC = (int)(rC.x & 0xFFFFu); if (mC == 0) mC = 65536;
+                offA = (int)(rA.y >> 16); offB = (int)(rB.y >> 16); offC = (int)(rC.y >> 16);
+                b1 = clamp08(mA - p);
+                b2 = vB ? clamp08(eA - p) : 8;
+                b3 = vB ? clamp08(mB - p) : 8;
+                b4 = (vB && vC) ? clamp08(eB - p) : 8;
+                b5 = (vB && vC) ? clamp08(mC - p) : 8;
+                /* literal pieces: no dependencies */
+                const uint64_t M1 = lowbytes(b1), M2 = lowbytes(b2), M3 = lowbytes(b3), M4 = lowbytes(b4), M5 = lowbytes(b5);
+                if (b1 > 0) acc = lds64u(S.in, head + (int)((p + rA.y) & 0xFFFFu)) & M1;
+                if (b3 > b2) {
+                    const int q0 = p + b2;                     // first byte of B: its input position is exact
+                    acc |= lds64u(S.in, head + (int)((q0 + rB.y) & 0xFFFFu) - b2) & (M3 ^ M2);
                 }
-                needMA = (nB > nA) && offA != 0;               // offset 0 decodes to zero bytes (lz4.c:2407)
-                needMB = (nC < 4) && offB != 0 && (nB < 4);
-                uint32_t LA = 0, LB = 0;
-                if (nA > 0) LA = lds32u(S.in, head + (int)((p + dA) & 0xFFFFu));
-                if (nC > nB) LB = lds32u(S.in, head + (int)((p + dB) & 0xFFFFu));
-                const uint32_t sA = shl_clamp(0xFFFFFFFFu, nA * 8), sB = shl_clamp(0xFFFFFFFFu, nB * 8);
-                word = (LA & ~sA) | (LB & sB);                 // literal bytes; match bytes are merged below
-                /* exact source words of the match pieces (periods < 4 take the careful path) */
-                slow = (needMA && offA < 4) || (needMB && offB < 4);
-                if (needMA) { w0a = (p + nA - offA) >> 2; w1a = (p + nB - offA - 1) >> 2; }
-                if (needMB) { w0b = (p + nC - offB) >> 2; w1b = (p + 3 - offB) >> 2; }
-                bool ready = !slow;
-                if (needMA) ready = ready && (((vWdone[w0a >> 5] >> (w0a & 31)) & (vWdone[w1a >> 5] >> (w1a & 31)) & 1u) != 0);
-                if (needMB) ready = ready && (((vWdone[w0b >> 5] >> (w0b & 31)) & (vWdone[w1b >> 5] >> (w1b & 31)) & 1u) != 0);
-                if (ready) {
-                    __threadfence_block();
-                    uint32_t MA = 0, MB = 0;
-                    if (needMA) MA = lds32u(S.out, p - offA);
-                    if (needMB) MB = lds32u(S.out, p - offB);
-                    const uint32_t sC = shl_clamp(0xFFFFFFFFu, nC * 8);
-                    word = (word & (~sA | (sB & ~sC))) | (MA & sA & ~sB) | (MB & sC);
-                    *reinterpret_cast<uint32_t*>(S.out + p) = word;
-                    done = true;
+                if (b5 > b4) {
+                    const int q0 = p + b4;
+                    acc |= lds64u(S.in, head + (int)((q0 + rC.y) & 0xFFFFu) - b4) & (M5 ^ M4);
                 }
+                needA = (b2 > b1) && offA != 0;                // offset 0 decodes to zero bytes (lz4.c:2407)
+                needB = (b4 > b3) && offB != 0;
+                needC = (b5 < 8) && offC != 0;
+                anyShort = (needA && offA < 8) || (needB && offB < 8) || (needC && offC < 8);
             }
-            __syncwarp();
-            unsigned dm = __ballot_sync(kFull, done);
-            if (lane == 0) { __threadfence_block(); vWdone[s] = dm; }
-            if (dm != kFull) {
-                /* careful path: poll the word-level flags of the exact source words; periods < 4 and
-                 * in-word dependencies go through the byte-serial routine */
-                if (!done && slow) {                           // sources of a period-<4 piece: [m - off, min(m, p))
-                    if (needMA && offA < 4) { const int sa = mA - offA, sb = min(mA, p); w0a = (sb > sa) ? (sa >> 2) : -1; w1a = (sb - 1) >> 2; }
-                    if (needMB && offB < 4) { const int sa = mB - offB, sb = min(mB, p); w0b = (sb > sa) ? (sa >> 2) : -1; w1b = (sb - 1) >> 2; }
-                }
-                for (;;) {
-                    if (!done) {
-                        bool ready = true;
-                        if (w0a >= 0) ready = ((vWdone[w0a >> 5] >> (w0a & 31)) & (vWdone[w1a >> 5] >> (w1a & 31)) & 1u) != 0;
-                        if (ready && w0b >= 0) ready = ((vWdone[w0b >> 5] >> (w0b & 31)) & (vWdone[w1b >> 5] >> (w1b & 31)) & 1u) != 0;
-                        if (ready) {
-                            __threadfence_block();             // flag reads before data reads
-                            if (!slow) {
-                                uint32_t MA = 0, MB = 0;
-                                if (needMA) MA = lds32u(S.out, p - offA);
-                                if (needMB) MB = lds32u(S.out, p - offB);
-                                const uint32_t sA = shl_clamp(0xFFFFFFFFu, nA * 8), sB = shl_clamp(0xFFFFFFFFu, nB * 8);
-                                const uint32_t sC = shl_clamp(0xFFFFFFFFu, nC * 8);
-                                word = (word & (~sA | (sB & ~sC))) | (MA & sA & ~sB) | (MB & sC);
-                            } else {
-                                word = assemble_bytewise(S.in + head, S.out, p, word, nA, nB, nC, mA, offA, mB, offB);
-                            }
-                            *reinterpret_cast<uint32_t*>(S.out + p) = word;
-                            done = true;
+            for (;;) {
+                if (pending) {
+                    bool blocked = false;
+                    uint64_t macc = 0;
+                    if (!anyShort) {
+                        /* flags of the source chunks of the three match pieces */
+                        if (needA) blocked |= !sources_ready(vDone8, p + b1 - offA, p + b2 - 1 - offA, ownChunk0);
+                        if (needB) blocked |= !sources_ready(vDone8, p + b3 - offB, p + b4 - 1 - offB, ownChunk0);
+                        if (needC) blocked |= !sources_ready(vDone8, p + b5 - offC, p + 7 - offC, ownChunk0);
+                        if (!blocked) {
+                            __threadfence_block();             // flags before data
+                            const uint64_t M1 = lowbytes(b1), M2 = lowbytes(b2), M3 = lowbytes(b3), M4 = lowbytes(b4), M5 = lowbytes(b5);
+                            if (needA) macc = lds64u(S.out, p - offA) & (M2 ^ M1);
+                            if (needB) macc |= lds64u(S.out, p - offB) & (M4 ^ M3);
+                            if (needC) macc |= lds64u(S.out, p - offC) & ~M5;
                         }
-                    }
-                    __syncwarp();
-                    const unsigned dm2 = __ballot_sync(kFull, done);
-                    if (dm2 != dm) {                           // publish the words finished this round
-                        if (lane == 0) { __threadfence_block(); vWdone[s] = dm2; }
-                        dm = dm2;
                     } else {
-                        __nanosleep(20);
+                        /* rare: some piece has a period < 8 (or reads this very chunk): byte-serial */
+                        macc = match_bytes_serial(S.out, vDone8, p, ownChunk0, acc, b1, b2, b3, b4, b5,
+                                                  mA, mB, mC, offA, offB, offC, needA, needB, needC, blocked);
                     }
-                    if (dm == kFull) break;
+                    if (!blocked) {
+                        *reinterpret_cast<uint64_t*>(S.out + p) = acc | macc;
+                        __threadfence_block();                 // data before flag
+                        vDone8[p >> 3] = 1;
+                        pending = false;
+                    }
                 }
+                if (!__any_sync(kFull, pending)) break;        // parked lanes retry after reconvergence
             }
         }
         __syncthreads();
@@ -586,6 +613,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
         } else {
             for (int k = tid; k < total; k += kFastThreads) dst[k] = S.out[k];
         }
+        PHASE_MARK(6);                                     // store issue
     }
     if (tid == 0) tma_wait_all0();
 }
@@ -889,6 +917,15 @@ __global__ void __launch_bounds__(256) lz4_pack_gather_kernel(const uint8_t* __r
 extern "C" {
 
 uint64_t lz4k_launch_count(void) { return g_launches; }
+
+/* debug: read and reset the phase-cycle counters (all zero unless built with -DLZ4K_PHASE_TIMING) */
+int lz4k_debug_phase_cycles(unsigned long long* out8)
+{
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyFromSymbol(out8, g_phaseCycles, sizeof(z));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_phaseCycles, z, sizeof(z));
+    return (int)e;
+}
 
 size_t lz4k_decode_workspace_bytes(int64_t nBlocks)
 {

@@ -48,6 +48,7 @@ int lz4k_launch_encode(const lz4k_encode_args* a, void* stream);
 int lz4k_launch_pack(const uint8_t* slots, int64_t slotStride, const int32_t* sizes, int64_t nBlocks,
                      uint8_t* packed, int64_t* outOff, int headerBytes, void* stream);
 uint64_t lz4k_launch_count(void);
+int lz4k_debug_phase_cycles(unsigned long long* out8);
 
 #ifdef __cplusplus
 }
