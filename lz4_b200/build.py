@@ -20,6 +20,8 @@ HEADERS = [os.path.join(CSRC, "lz4_kernels.h"), os.path.join(ROOT, "include", "l
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math", "-diag-suppress", "177"]
+if os.environ.get("LZ4K_FAST_THREADS"):        # developer knob: CTA size of the fast expand kernel
+    NVCC_FLAGS.append("-DLZ4K_FAST_THREADS=" + os.environ["LZ4K_FAST_THREADS"])
 if os.environ.get("LZ4K_PHASE_TIMING"):          # developer build: per-phase clock64 counters
     NVCC_FLAGS.append("-DLZ4K_PHASE_TIMING")
 CC_FLAGS = ["-O2", "-fPIC", "-std=c99", "-Wall", "-Wextra", "-fvisibility=hidden",

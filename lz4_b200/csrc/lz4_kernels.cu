@@ -40,6 +40,7 @@ __device__ unsigned long long g_phaseCycles[8];
 #endif
 
 __device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return __ldg(p); }
+__device__ __forceinline__ void prefetch_l1(const uint8_t* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return __ldg(p) | (__ldg(p + 1) << 8); }
 
 /* unaligned little-endian 32-bit read through two aligned words (never touches a word that holds
@@ -89,14 +90,15 @@ __device__ __forceinline__ bool read_runlength(const uint8_t* src, int64_t& ip, 
 /* Checkpoint = where the first token at or after input byte 256*j starts: (token position, output
  * position, sequence index).  The expand kernel's lanes restart the token walk from these. */
 struct __align__(8) Checkpoint { uint16_t tok, op, seq, pad; };
-constexpr int kCkStride = 256;
-constexpr int kCkSlots = 256;                  // enough for inputs <= 65535 bytes
+constexpr int kCkShift = 7;
+constexpr int kCkStride = 1 << kCkShift;       // one checkpoint slot per 128 input bytes
+constexpr int kCkSlots = 65536 >> kCkShift;    // enough for inputs <= 65535 bytes
 constexpr uint16_t kCkEmpty = 0xFFFF;
 
 #define CK_VISIT()                                                                              \
     do {                                                                                        \
-        if (ck && (ip >> 8) >= nextSlot) {                                                      \
-            const int64_t slot = ip >> 8;                                                       \
+        if (ck && (ip >> kCkShift) >= nextSlot) {                                               \
+            const int64_t slot = ip >> kCkShift;                                                       \
             Checkpoint c; c.tok = kCkEmpty; c.op = 0; c.seq = 0; c.pad = 0;                     \
             while (nextSlot < slot && nextSlot < kCkSlots) ck[nextSlot++] = c;                  \
             if (slot < kCkSlots && op < 65536 && nseq < 65536) {                                \
@@ -109,7 +111,7 @@ constexpr uint16_t kCkEmpty = 0xFFFF;
 
 __device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut, Checkpoint* ck)
 {
-    int64_t nextSlot = 0;
+    int64_t nextSlot = 0, nextPrefetch = 128;
     int64_t n = nIn, cap = capIn, ip = 0, op = 0, ll = 0, ml = 0, add = 0;
     uint32_t token = 0, offset = 0, nseq = 0;
     bool fast;
@@ -121,6 +123,10 @@ __device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, u
 
     for (;;) {
         CK_VISIT();
+        if (ip + 128 >= nextPrefetch) {                               // keep the input one 128-byte line ahead in L1
+            if (ip + 128 < n) prefetch_l1(src + ip + 128);
+            nextPrefetch = ip + 256;
+        }
         token = ldb(src + ip); ip++;
         ll = token >> 4;
         ml = token & 15;
@@ -164,7 +170,7 @@ safe_literals:
             *nSeqOut = nseq;
             if (ck) {                                                  // slots no token starts in
                 Checkpoint c; c.tok = kCkEmpty; c.op = 0; c.seq = 0; c.pad = 0;
-                const int64_t lastSlot = (n - 1) >> 8;
+                const int64_t lastSlot = (n - 1) >> kCkShift;
                 while (nextSlot <= lastSlot && nextSlot < kCkSlots) ck[nextSlot++] = c;
             }
             return (int)op;                                            // lz4.c:2439
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(128) lz4_expand_generic_kernel(lz4k_decode_arg
  * expand (fast): one CTA per 64 KB block, everything staged in shared memory
  *
  *   TMA bulk load  : compressed block  HBM -> smem            (cp.async.bulk + mbarrier)
- *   phase A        : one LANE per 256-byte input slot restarts the token walk at the scan's
+ *   phase A        : one LANE per 128-byte input slot restarts the token walk at the scan's
  *                    checkpoint and writes an 8-byte record per sequence + a start-bit per
  *                    sequence (bit index = output position)
  *   rank           : exclusive scan of the popcounts of the start bits (sequence index of a byte =
@@ -283,7 +289,10 @@ __global__ void __launch_bounds__(128) lz4_expand_generic_kernel(lz4k_decode_arg
  *   TMA bulk store : decoded block  smem -> HBM              (cp.async.bulk.global.shared::cta)
  * HBM traffic is exactly the algorithmic bytes (C_i in, U_i out) plus the checkpoints.
  * ============================================================================================= */
-constexpr int kFastThreads = 1024;
+#ifndef LZ4K_FAST_THREADS
+#define LZ4K_FAST_THREADS 1024
+#endif
+constexpr int kFastThreads = LZ4K_FAST_THREADS;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kInBytes = 65536 + 64;
 
@@ -297,7 +306,7 @@ struct FastSmem {
     uint16_t seqbase[2048];                         // number of starts before bits[i]
     uint32_t warpSum[32];
     alignas(8) uint64_t mbar;
-    uint32_t curIdx;
+    uint32_t nextIdx[2];                            // work-list cursor values, fetched one block ahead
     alignas(16) uint8_t done8[8192];                // done8[c] != 0: output bytes [8c, 8c+8) are final
 };
 
@@ -332,6 +341,7 @@ __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commi
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
 
 
@@ -344,66 +354,8 @@ __device__ __forceinline__ uint64_t lds64u(const uint8_t* base, int idx)
     return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
 }
 
-__device__ __forceinline__ int clamp08(int v) { return min(8, max(v, 0)); }
 
-/* shl.b32 clamps shift amounts >= 32 to a zero result (C's << does not) */
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, int sh)
-{
-    uint32_t r;
-    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));
-    return r;
-}
-/* 64-bit mask of the low b bytes, b in [0, 8] */
-__device__ __forceinline__ uint64_t lowbytes(int b)
-{
-    const uint32_t lo = ~shl_clamp(0xFFFFFFFFu, 8 * b);
-    const uint32_t hi = ~shl_clamp(0xFFFFFFFFu, max(8 * b - 32, 0));
-    return (uint64_t)lo | ((uint64_t)hi << 32);
-}
 
-/* Are output bytes [lo, hi] (hi - lo < 8, both below the caller's chunk) final?  Chunks that belong
- * to other warps are waited for; chunks of the caller's own strip only polled (see phase B). */
-__device__ __forceinline__ bool sources_ready(const volatile uint8_t* done8, int lo, int hi, int ownChunk0)
-{
-    const int c0 = lo >> 3, c1 = hi >> 3;
-    if (c1 >= ownChunk0) return (done8[c0] & done8[c1]) != 0;
-    while (!(done8[c0] & done8[c1])) { }
-    return true;
-}
-
-/* Rare path of phase B: the match bytes of one chunk built one at a time, for pieces whose period
- * is < 8.  Byte x of a match starting at m with offset off reads x - off, or -- when that is inside
- * the match itself -- m - off + ((x - m) mod off), which is always before the match start.  Sources
- * inside this chunk (>= p) come from the bytes assembled so far. */
-__device__ __noinline__ uint64_t match_bytes_serial(const uint8_t* out, const volatile uint8_t* done8, int p, int ownChunk0,
-                                                     uint64_t lit, int b1, int b2, int b3, int b4, int b5,
-                                                     int mA, int mB, int mC, int offA, int offB, int offC,
-                                                     bool needA, bool needB, bool needC, bool& blocked)
-{
-    uint64_t v = 0;
-    for (int i = 0; i < 8; i++) {
-        int m, off;
-        if (i >= b1 && i < b2) { if (!needA) continue; m = mA; off = offA; }
-        else if (i >= b3 && i < b4) { if (!needB) continue; m = mB; off = offB; }
-        else if (i >= b5) { if (!needC) continue; m = mC; off = offC; }
-        else continue;                                         // literal byte
-        const int x = p + i;
-        int sidx = x - off;
-        if (sidx >= m) sidx = m - off + ((x - m) % off);
-        uint32_t byte;
-        if (sidx >= p) {
-            byte = (uint32_t)(((lit | v) >> (8 * (sidx - p))) & 0xFFu);
-        } else {
-            const int c = sidx >> 3;
-            if (c >= ownChunk0) { if (!done8[c]) { blocked = true; return 0; } }
-            else { while (!done8[c]) { } }
-            __threadfence_block();
-            byte = out[sidx];
-        }
-        v |= (uint64_t)byte << (8 * i);
-    }
-    return v;
-}
 
 __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_decode_args a)
 {
@@ -421,11 +373,13 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
     long long tPhase = clock64();
 #endif
 
-    for (;;) {
-        if (tid == 0) S.curIdx = atomicAdd(&w.hdr->fastCursor, 1u);
-        __syncthreads();
-        const uint32_t idx = S.curIdx;
+    if (tid == 0) S.nextIdx[0] = atomicAdd(&w.hdr->fastCursor, 1u);
+    __syncthreads();
+
+    for (uint32_t it = 0;; it++) {
+        const uint32_t idx = S.nextIdx[it & 1];
         if (idx >= fastCount) break;
+        if (tid == 0) S.nextIdx[(it + 1) & 1] = atomicAdd(&w.hdr->fastCursor, 1u);   // read after this block's barriers
         const int64_t b = w.fastList[idx];
         const uint8_t* src = a.src + a.srcOff[b];
         const int n = a.srcSize[b];
@@ -441,8 +395,13 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                 tma_load_1d(S.in + o, src - head + o, min(16384u, loadBytes - o), &S.mbar);
         }
         for (int k = tid; k < 2048; k += kFastThreads) S.bits[k] = 0;
-        reinterpret_cast<uint64_t*>(S.done8)[tid] = 0;          // kFastThreads * 8 == 8192
+        for (int k = tid; k < 1024; k += kFastThreads) reinterpret_cast<uint64_t*>(S.done8)[k] = 0;
         __syncthreads();
+        /* this lane's checkpoint (phase A), fetched while the TMA load is in flight */
+        const int nslots = (n + kCkStride - 1) >> kCkShift;
+        Checkpoint ckpt; ckpt.tok = kCkEmpty; ckpt.op = 0; ckpt.seq = 0; ckpt.pad = 0;
+        if (tid < nslots) ckpt = w.ck[b * kCkSlots + tid];
+        static_assert(kFastThreads >= kCkSlots, "phase A uses one lane per checkpoint slot");
         PHASE_MARK(0);                                     // fetch + zeroing
         while (!mbar_try_wait(&S.mbar, parity)) { }
         parity ^= 1;
@@ -451,9 +410,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
         /* ---- phase A: sequence records + start bits ---- */
         const uint8_t* in = S.in + head;
         {
-            const int nslots = (n + kCkStride - 1) / kCkStride;
             if (tid < nslots) {
-                const Checkpoint c = w.ck[b * kCkSlots + tid];
+                const Checkpoint c = ckpt;
                 if (c.tok != kCkEmpty) {
                     int tok = c.tok, op = c.op, k = c.seq;
                     const int limit = (tid + 1) * kCkStride;
@@ -516,89 +474,93 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
         }
         __syncthreads();
 
-        /* ---- phase B: assemble the output, one aligned 8-byte chunk per lane ----
-         * An 8-byte chunk intersects at most three sequences (every sequence but the last is >= 4
-         * bytes long): A covers its first byte, then B, then C -- hence at most six pieces
-         * A.lit A.match B.lit B.match C.lit C.match with boundaries b1..b5 (bytes from the chunk
-         * start).  The source of output byte q is in[q + delta] for literals and out[q - offset] for
-         * matches, so each piece is ONE unaligned 8-byte load at the chunk's own position and a byte
-         * mask -- no loop, no shifting.  A match piece needs the done-flags of the (at most two)
-         * chunks holding its source bytes: chunks of other warps are waited for in place; chunks of
-         * this warp's own strip (lower lanes) cannot be spun on inside divergent code, so the lane
-         * parks and retries after the warp has reconverged. */
-        const int nstrips = (total + 255) >> 8;
-        for (int s = warp; s < nstrips; s += kFastWarps) {
-            const int p = (s << 8) + (lane << 3);
-            const int ownChunk0 = s << 5;                      // first chunk of this warp's strip
-            bool pending = p < total;
+        /* ---- phase B: assemble the output in aligned 8-byte chunks ----
+         * Lane L of warp w owns the chunks at w*256 + L*8 + i*(32 warps * 256): at any moment the
+         * CTA works on an 8 KB window that slides forward, so almost all match sources are final
+         * long before they are needed.  The loop is FLATTENED: one iteration handles one PIECE
+         * (literal run or match run clipped to the chunk) per lane -- one unaligned 8-byte read from
+         * the staged input (literals) or the output window (match), masked and shifted into place --
+         * and a lane that finishes its chunk moves on to its next one at once, so lanes with many
+         * small pieces do not stall the others.  A match piece whose source chunks are not flagged
+         * done simply does not advance in this iteration (no spin loops, no warp-level barriers). */
+        {
+            const int laneStride = kFastWarps << 8;
+            int p = (warp << 8) + (lane << 3);
+            bool active = p < total;
+            int pe = 0, k = 0, m = 0, e = 0, off = 0, pos = 0;
+            uint32_t d = 0;
             uint64_t acc = 0;
-            int b1 = 8, b2 = 8, b3 = 8, b4 = 8, b5 = 8;
-            int mA = 0, mB = 0, mC = 0, offA = 0, offB = 0, offC = 0;
-            bool needA = false, needB = false, needC = false, anyShort = false;
-            if (pending) {
-                const uint32_t bw = S.bits[p >> 5];
-                const int kA = (int)S.seqbase[p >> 5] + __popc(bw & (0xFFFFFFFFu >> (31 - (p & 31)))) - 1;
-                const uint2 rA = S.rec[kA], rB = S.rec[kA + 1], rC = S.rec[kA + 2];
-                const bool vB = kA + 1 < nseq, vC = kA + 2 < nseq;
-                mA = (int)(rA.x & 0xFFFFu); if (mA == 0 && kA != 0) mA = 65536;      // 16-bit wrap of 65536
-                int eA = (int)(rA.x >> 16); if (eA == 0) eA = 65536;
-                mB = (int)(rB.x & 0xFFFFu); if (mB == 0) mB = 65536;
-                int eB = (int)(rB.x >> 16); if (eB == 0) eB = 65536;
-                mC = (int)(rC.x & 0xFFFFu); if (mC == 0) mC = 65536;
-                offA = (int)(rA.y >> 16); offB = (int)(rB.y >> 16); offC = (int)(rC.y >> 16);
-                b1 = clamp08(mA - p);
-                b2 = vB ? clamp08(eA - p) : 8;
-                b3 = vB ? clamp08(mB - p) : 8;
-                b4 = (vB && vC) ? clamp08(eB - p) : 8;
-                b5 = (vB && vC) ? clamp08(mC - p) : 8;
-                /* literal pieces: no dependencies */
-                const uint64_t M1 = lowbytes(b1), M2 = lowbytes(b2), M3 = lowbytes(b3), M4 = lowbytes(b4), M5 = lowbytes(b5);
-                if (b1 > 0) acc = lds64u(S.in, head + (int)((p + rA.y) & 0xFFFFu)) & M1;
-                if (b3 > b2) {
-                    const int q0 = p + b2;                     // first byte of B: its input position is exact
-                    acc |= lds64u(S.in, head + (int)((q0 + rB.y) & 0xFFFFu) - b2) & (M3 ^ M2);
-                }
-                if (b5 > b4) {
-                    const int q0 = p + b4;
-                    acc |= lds64u(S.in, head + (int)((q0 + rC.y) & 0xFFFFu) - b4) & (M5 ^ M4);
-                }
-                needA = (b2 > b1) && offA != 0;                // offset 0 decodes to zero bytes (lz4.c:2407)
-                needB = (b4 > b3) && offB != 0;
-                needC = (b5 < 8) && offC != 0;
-                anyShort = (needA && offA < 8) || (needB && offB < 8) || (needC && offC < 8);
-            }
-            for (;;) {
-                if (pending) {
-                    bool blocked = false;
-                    uint64_t macc = 0;
-                    if (!anyShort) {
-                        /* flags of the source chunks of the three match pieces */
-                        if (needA) blocked |= !sources_ready(vDone8, p + b1 - offA, p + b2 - 1 - offA, ownChunk0);
-                        if (needB) blocked |= !sources_ready(vDone8, p + b3 - offB, p + b4 - 1 - offB, ownChunk0);
-                        if (needC) blocked |= !sources_ready(vDone8, p + b5 - offC, p + 7 - offC, ownChunk0);
-                        if (!blocked) {
-                            __threadfence_block();             // flags before data
-                            const uint64_t M1 = lowbytes(b1), M2 = lowbytes(b2), M3 = lowbytes(b3), M4 = lowbytes(b4), M5 = lowbytes(b5);
-                            if (needA) macc = lds64u(S.out, p - offA) & (M2 ^ M1);
-                            if (needB) macc |= lds64u(S.out, p - offB) & (M4 ^ M3);
-                            if (needC) macc |= lds64u(S.out, p - offC) & ~M5;
+            #define LOAD_CHUNK()                                                                         \
+                do {                                                                                     \
+                    pe = min(p + 8, total);                                                              \
+                    const uint32_t bw_ = S.bits[p >> 5];                                                 \
+                    k = (int)S.seqbase[p >> 5] + __popc(bw_ & (0xFFFFFFFFu >> (31 - (p & 31)))) - 1;     \
+                    const uint2 r_ = S.rec[k];                                                           \
+                    m = (int)(r_.x & 0xFFFFu); e = (int)(r_.x >> 16); off = (int)(r_.y >> 16);            \
+                    d = r_.y & 0xFFFFu;                                                                  \
+                    if (m == 0 && k != 0) m = 65536;             /* 16-bit wrap of 65536 */              \
+                    if (e == 0) e = 65536;                                                               \
+                    pos = p; acc = 0;                                                                    \
+                } while (0)
+            if (active) LOAD_CHUNK();
+            while (__any_sync(kFull, active)) {
+                if (active) {
+                    bool ok = true;
+                    uint64_t v = 0;
+                    int end;
+                    if (pos < m) {                             // literal piece
+                        end = min(m, pe);
+                        v = lds64u(S.in, head + (int)((pos + d) & 0xFFFFu));
+                    } else {                                   // match piece
+                        end = min(e, pe);
+                        if (off >= 8) {
+                            const int src = pos - off;
+                            ok = (vDone8[src >> 3] & vDone8[(end - 1 - off) >> 3]) != 0;
+                            if (ok) { fence_acq_rel_cta(); v = lds64u(S.out, src); }   // flags before data
+                        } else if (off != 0) {                 // short period or source inside this chunk
+                            #pragma unroll 1
+                            for (int x = pos; x < end; x++) {
+                                int sidx = x - off;
+                                if (sidx >= m) sidx = m - off + ((x - m) % off);       // always before the match
+                                uint32_t byte;
+                                if (sidx >= p) {
+                                    byte = (uint32_t)((acc >> (8 * (sidx - p))) & 0xFFu);
+                                } else {
+                                    if (!vDone8[sidx >> 3]) { ok = false; break; }
+                                    fence_acq_rel_cta();
+                                    byte = S.out[sidx];
+                                }
+                                v |= (uint64_t)byte << (8 * (x - pos));
+                            }
+                        }                                      // off == 0: zero bytes (lz4.c:2407)
+                    }
+                    if (ok) {
+                        const int len = end - pos;
+                        v &= 0xFFFFFFFFFFFFFFFFull >> (64 - 8 * len);
+                        acc |= v << (8 * (pos - p));
+                        pos = end;
+                        if (pos >= pe) {                       // chunk complete: publish, take the next one
+                            *reinterpret_cast<uint64_t*>(S.out + p) = acc;
+                            fence_acq_rel_cta();               // data before flag
+                            vDone8[p >> 3] = 1;
+                            p += laneStride;
+                            active = p < total;
+                            if (active) LOAD_CHUNK();
+                        } else if (pos == e) {                 // next sequence starts inside this chunk
+                            k++;
+                            const uint2 r = S.rec[k];
+                            m = (int)(r.x & 0xFFFFu); e = (int)(r.x >> 16); off = (int)(r.y >> 16);
+                            d = r.y & 0xFFFFu;
+                            if (m == 0) m = 65536;
+                            if (e == 0) e = 65536;
                         }
-                    } else {
-                        /* rare: some piece has a period < 8 (or reads this very chunk): byte-serial */
-                        macc = match_bytes_serial(S.out, vDone8, p, ownChunk0, acc, b1, b2, b3, b4, b5,
-                                                  mA, mB, mC, offA, offB, offC, needA, needB, needC, blocked);
-                    }
-                    if (!blocked) {
-                        *reinterpret_cast<uint64_t*>(S.out + p) = acc | macc;
-                        __threadfence_block();                 // data before flag
-                        vDone8[p >> 3] = 1;
-                        pending = false;
                     }
                 }
-                if (!__any_sync(kFull, pending)) break;        // parked lanes retry after reconvergence
             }
+            #undef LOAD_CHUNK
         }
         __syncthreads();
+        PHASE_MARK(5);                                     // phase B
 
         /* ---- store: smem -> HBM ---- */
         if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
