@@ -169,6 +169,44 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local):
+    """Host-side tuning for the e2e leg: run (and first-touch / pin host buffers) on the CPU cores of
+    the NUMA node the GPU hangs off, so pinned-memory PCIe copies do not cross the socket link."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "cpus": len(ids)}
+    except Exception:
+        return None
+
+
+def pcie_probe(torch, device, nbytes=1 << 30):
+    """Plain pinned-memory copy rates (GB/s) on this box: the ceiling of any host-buffer path."""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    res = {}
+    for name, dst, src in (("h2d", d, h), ("d2h", h, d)):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        res[name] = round(3 * nbytes / (time.perf_counter() - t0) / GB, 2)
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -270,6 +308,8 @@ def run_ours(args):
     # ---- e2e: same workload through the host-buffer C-ABI call, pinned host memory ----
     e2e = None
     if not args.no_e2e:
+        all_cpus = os.sched_getaffinity(0)
+        numa = bind_to_gpu_numa_node(torch, local)      # pin + first-touch the host buffers next to the GPU
         h_comp = torch.empty(comp_bytes + 16, dtype=torch.uint8, pin_memory=True)
         h_comp.copy_(packed[:comp_bytes + 16])
         h_offs = offs.cpu().numpy()
@@ -293,10 +333,13 @@ def run_ours(args):
             t = torch.tensor([dt], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        pcie = pcie_probe(torch, device)
         e2e = {"value": round(world * total * args.e2e_steps / dt / GB, 3), "unit": "GB/s",
+               "pcie_pinned_copy_GBps": pcie, "host_numa_binding": numa,
                "h2d_bytes_per_step": int(comp_bytes + n_blocks * 12), "d2h_bytes_per_step": int(total + n_blocks * 4),
                "steps": args.e2e_steps, "api": "LZ4B200_decompress_blocks_host (pinned host buffers)"}
         del h_comp, h_out
+        os.sched_setaffinity(0, all_cpus)
     sampler.stop()
 
     # ---- reassembly (multi-GPU only): one in-place NCCL all-gather of the decoded shards ----
