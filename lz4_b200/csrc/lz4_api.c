@@ -61,6 +61,10 @@ typedef struct {
     void* d_out[N_PIPE];  size_t out_cap[N_PIPE];
     void* d_meta[N_PIPE]; size_t meta_cap[N_PIPE];
     void* d_ws[N_PIPE];   size_t ws_cap[N_PIPE];
+    /* pinned host staging for the per-block tables, so that every copy of a chunk is truly
+     * asynchronous (a pageable cudaMemcpyAsync blocks the host and serialises the pipeline) */
+    void* h_meta[N_PIPE]; size_t hmeta_cap[N_PIPE];
+    int32_t* pend_dst[N_PIPE]; int64_t pend_cnt[N_PIPE];   /* return values still to be handed to the caller */
 } host_ctx;
 
 static host_ctx g_ctx;
@@ -77,6 +81,29 @@ static int ctx_init(void)
     g_ctx.ready = 1;
 done:
     return rc;
+}
+
+static int grow_pinned(void** p, size_t* cap, size_t need)
+{
+    int rc = LZ4B200_OK;
+    if (need <= *cap) return rc;
+    if (*p) { CU(cudaFreeHost(*p)); *p = NULL; *cap = 0; }
+    need = (need + 65535) & ~(size_t)65535;
+    CU(cudaHostAlloc(p, need, cudaHostAllocDefault));
+    *cap = need;
+done:
+    return rc;
+}
+
+/* hand the return values of the chunk that last used `slot` to the caller (its stream is idle) */
+static void flush_slot(int slot)
+{
+    if (g_ctx.pend_dst[slot]) {
+        const int64_t cnt = g_ctx.pend_cnt[slot];
+        const int32_t* h_ret = (const int32_t*)((char*)g_ctx.h_meta[slot] + (size_t)cnt * (sizeof(int64_t) + sizeof(int32_t)));
+        memcpy(g_ctx.pend_dst[slot], h_ret, (size_t)cnt * sizeof(int32_t));
+        g_ctx.pend_dst[slot] = NULL;
+    }
 }
 
 static int grow(void** p, size_t* cap, size_t need)
@@ -179,7 +206,6 @@ int LZ4B200_decompress_blocks_host(const void* h_src, const int64_t* h_srcOff, c
         cudaStream_t st = g_ctx.stream[slot];
         int64_t lo = h_srcOff[first], hi = lo, k;
         size_t inBytes, outBytes = (size_t)(cnt * dstStride), metaBytes, wsBytes;
-        int64_t* relOff;
         /* the chunk's compressed bytes span [lo, hi) of h_src (blocks may be in any order) */
         for (k = first; k < first + cnt; k++) {
             if (h_srcSize[k] < 0) { rc = LZ4B200_ERR_ARG; goto done; }
@@ -190,33 +216,37 @@ int LZ4B200_decompress_blocks_host(const void* h_src, const int64_t* h_srcOff, c
         metaBytes = (size_t)cnt * (sizeof(int64_t) + 2 * sizeof(int32_t));
         wsBytes = lz4k_decode_workspace_bytes(cnt);
         CU(cudaStreamSynchronize(st));                      /* slot reuse: previous chunk on it is finished */
+        flush_slot(slot);
         if ((rc = grow(&g_ctx.d_in[slot], &g_ctx.in_cap[slot], inBytes + 16)) != LZ4B200_OK) goto done;
         if ((rc = grow(&g_ctx.d_out[slot], &g_ctx.out_cap[slot], outBytes + 16)) != LZ4B200_OK) goto done;
         if ((rc = grow(&g_ctx.d_meta[slot], &g_ctx.meta_cap[slot], metaBytes + 16)) != LZ4B200_OK) goto done;
         if ((rc = grow(&g_ctx.d_ws[slot], &g_ctx.ws_cap[slot], wsBytes)) != LZ4B200_OK) goto done;
+        if ((rc = grow_pinned(&g_ctx.h_meta[slot], &g_ctx.hmeta_cap[slot], metaBytes + 16)) != LZ4B200_OK) goto done;
         {
             int64_t* d_off = (int64_t*)g_ctx.d_meta[slot];
             int32_t* d_size = (int32_t*)(d_off + cnt);
             int32_t* d_ret = d_size + cnt;
-            /* offsets relative to the chunk's first byte: staged through the (pageable) output-size
-             * array is not possible, so rebase on the fly into a small host vector */
-            relOff = (int64_t*)malloc((size_t)cnt * sizeof(int64_t));
-            if (!relOff) { rc = LZ4B200_ERR_ARG; goto done; }
-            for (k = 0; k < cnt; k++) relOff[k] = h_srcOff[first + k] - lo;
-            CU(cudaMemcpyAsync(d_off, relOff, (size_t)cnt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-            CU(cudaStreamSynchronize(st));                  /* relOff is pageable: copy done before free */
-            free(relOff);
-            CU(cudaMemcpyAsync(d_size, h_srcSize + first, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            int64_t* h_off = (int64_t*)g_ctx.h_meta[slot];          /* pinned: [offsets | sizes | return values] */
+            int32_t* h_size = (int32_t*)(h_off + cnt);
+            int32_t* h_ret = h_size + cnt;
+            for (k = 0; k < cnt; k++) h_off[k] = h_srcOff[first + k] - lo;   /* relative to the chunk's first byte */
+            memcpy(h_size, h_srcSize + first, (size_t)cnt * sizeof(int32_t));
+            CU(cudaMemcpyAsync(d_off, h_off, (size_t)cnt * (sizeof(int64_t) + sizeof(int32_t)), cudaMemcpyHostToDevice, st));
             CU(cudaMemcpyAsync(g_ctx.d_in[slot], (const char*)h_src + lo, inBytes, cudaMemcpyHostToDevice, st));
             rc = LZ4B200_decompress_blocks(g_ctx.d_in[slot], d_off, d_size, g_ctx.d_out[slot], NULL, dstStride,
                                            NULL, dstCap, d_ret, cnt, g_ctx.d_ws[slot], g_ctx.ws_cap[slot], st);
             if (rc != LZ4B200_OK) goto done;
             CU(cudaMemcpyAsync((char*)h_dst + first * dstStride, g_ctx.d_out[slot], outBytes, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(h_outSize + first, d_ret, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_ret, d_ret, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            g_ctx.pend_dst[slot] = h_outSize + first;
+            g_ctx.pend_cnt[slot] = cnt;
         }
     }
-    for (i = 0; i < N_PIPE; i++) CU(cudaStreamSynchronize(g_ctx.stream[i]));
+    for (i = 0; i < N_PIPE; i++) { CU(cudaStreamSynchronize(g_ctx.stream[i])); flush_slot(i); }
+    goto unlock;
 done:
+    for (i = 0; i < N_PIPE; i++) { cudaStreamSynchronize(g_ctx.stream[i]); g_ctx.pend_dst[i] = NULL; }
+unlock:
     pthread_mutex_unlock(&g_lock);
     return rc;
 }
