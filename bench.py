@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--gib", type=float, default=4.0, help="uncompressed GiB per GPU")
     ap.add_argument("--proba", type=float, default=0.5, help="datagen match probability (P50)")
     ap.add_argument("--accel", type=int, default=1)
+    ap.add_argument("--block-kb", type=int, default=64, help="block size in KB (64 = BASELINE configs 1-3; 4096 = lz4frame 4 MB blocks)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -147,15 +148,15 @@ def run_reference(args):
         t_total += t
     assert (out == data).all(), "reference round trip mismatch"
     value = n_blocks * BLOCK * args.steps / t_total / GB
-    sample = "%d blocks of 64 KB (%.2f GiB) datagen P%d, all %d host threads, static partition" % (
-        n_blocks, n_blocks * BLOCK / (1 << 30), round(args.proba * 100), cores)
+    sample = "%d blocks of %d KB (%.2f GiB) datagen P%d, all %d host threads, static partition" % (
+        n_blocks, BLOCK // 1024, n_blocks * BLOCK / (1 << 30), round(args.proba * 100), cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 * t_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "decompress %d x 64 KB blocks, datagen P%d, CPU %s lib/lz4.c" % (
-            n_blocks, round(args.proba * 100), kind), "block_bytes": BLOCK, "blocks": n_blocks,
+        "config": {"workload": "decompress %d x %d KB blocks, datagen P%d, CPU %s lib/lz4.c" % (
+            n_blocks, BLOCK // 1024, round(args.proba * 100), kind), "block_bytes": BLOCK, "blocks": n_blocks,
             "ratio": round(n_blocks * BLOCK / float(csz.sum()), 4)},
         "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample,
                          "compress_GBps_all_threads": round(n_blocks * BLOCK / tc / GB, 3)},
@@ -370,7 +371,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         _, codec, kind = cpu_codec()
-        nb = min(n_blocks, 16384)
+        nb = min(n_blocks, max(1, (1 << 30) // BLOCK))
         hi = int(offs_all[nb].item())
         comp_host = packed[:hi + 16].cpu().numpy()
         offs_host = offs[:nb].cpu().numpy()
@@ -405,9 +406,9 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": K,
         "warmup": max(args.warmup, 3), "ms_per_step": round(elapsed_ms / K, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "decompress-only, %d independent 64 KB blocks per GPU (%.2f GiB), tests/datagen P%d "
+        "config": {"workload": "decompress-only, %d independent %d KB blocks per GPU (%.2f GiB), tests/datagen P%d "
                                "(RDG_genBuffer per 64 MiB segment, seed=rank*64+k), compressed by LZ4_compress_fast accel %d"
-                               % (n_blocks, args.gib, round(args.proba * 100), args.accel),
+                               % (n_blocks, BLOCK // 1024, args.gib, round(args.proba * 100), args.accel),
                    "block_bytes": BLOCK, "blocks_per_gpu": n_blocks, "ratio": round(total / comp_bytes, 4),
                    "l2": "inputs (%.1f GiB compressed + %.1f GiB output per step) exceed the 126 MB L2; no flush needed"
                          % (comp_bytes / (1 << 30), total / (1 << 30)),
@@ -436,7 +437,11 @@ def run_ours(args):
 
 
 def main():
+    global BLOCK, METRIC
     args = parse_args()
+    if args.block_kb != 64:
+        BLOCK = args.block_kb * 1024
+        METRIC = METRIC.replace("64 KB", "%d KB" % args.block_kb)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

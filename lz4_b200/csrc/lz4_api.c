@@ -272,25 +272,26 @@ int LZ4B200_compress_blocks_host(const void* h_src, int64_t srcStride, int32_t s
         cudaStream_t st = g_ctx.stream[slot];
         size_t inBytes = (size_t)((cnt - 1) * srcStride + (isLast ? lastSize : srcSize));
         size_t slotBytes = (size_t)(cnt * dstStride);
-        size_t metaBytes = (size_t)cnt * 2 * sizeof(int32_t);
-        int32_t* d_sizes; int32_t* d_ret;
+        /* same table layout as the decode call: [unused i64 | source sizes i32 | return values i32] */
+        size_t metaBytes = (size_t)cnt * (sizeof(int64_t) + 2 * sizeof(int32_t));
+        int32_t *d_sizes, *d_ret, *h_sizes, *h_ret;
+        int64_t k;
         CU(cudaStreamSynchronize(st));
+        flush_slot(slot);
         if ((rc = grow(&g_ctx.d_in[slot], &g_ctx.in_cap[slot], inBytes + 16)) != LZ4B200_OK) goto done;
         if ((rc = grow(&g_ctx.d_out[slot], &g_ctx.out_cap[slot], slotBytes + 16)) != LZ4B200_OK) goto done;
         if ((rc = grow(&g_ctx.d_meta[slot], &g_ctx.meta_cap[slot], metaBytes + 16)) != LZ4B200_OK) goto done;
-        d_sizes = (int32_t*)g_ctx.d_meta[slot];
+        if ((rc = grow_pinned(&g_ctx.h_meta[slot], &g_ctx.hmeta_cap[slot], metaBytes + 16)) != LZ4B200_OK) goto done;
+        d_sizes = (int32_t*)((int64_t*)g_ctx.d_meta[slot] + cnt);
         d_ret = d_sizes + cnt;
+        h_sizes = (int32_t*)((int64_t*)g_ctx.h_meta[slot] + cnt);
+        h_ret = h_sizes + cnt;
         if (inBytes) CU(cudaMemcpyAsync(g_ctx.d_in[slot], (const char*)h_src + first * srcStride, inBytes, cudaMemcpyHostToDevice, st));
         if (isLast && lastSize != srcSize) {
             /* per-block size table only needed for the ragged final block */
-            int32_t* tmp = (int32_t*)malloc((size_t)cnt * sizeof(int32_t));
-            int64_t k;
-            if (!tmp) { rc = LZ4B200_ERR_ARG; goto done; }
-            for (k = 0; k < cnt; k++) tmp[k] = srcSize;
-            tmp[cnt - 1] = (int32_t)lastSize;
-            CU(cudaMemcpyAsync(d_sizes, tmp, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            CU(cudaStreamSynchronize(st));
-            free(tmp);
+            for (k = 0; k < cnt; k++) h_sizes[k] = srcSize;
+            h_sizes[cnt - 1] = (int32_t)lastSize;
+            CU(cudaMemcpyAsync(d_sizes, h_sizes, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             rc = LZ4B200_compress_blocks(g_ctx.d_in[slot], srcStride, d_sizes, srcSize, g_ctx.d_out[slot], dstStride,
                                          dstCap, acceleration, d_ret, cnt, st);
         } else {
@@ -299,10 +300,15 @@ int LZ4B200_compress_blocks_host(const void* h_src, int64_t srcStride, int32_t s
         }
         if (rc != LZ4B200_OK) goto done;
         CU(cudaMemcpyAsync((char*)h_dst + first * dstStride, g_ctx.d_out[slot], slotBytes, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h_outSize + first, d_ret, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_ret, d_ret, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        g_ctx.pend_dst[slot] = h_outSize + first;
+        g_ctx.pend_cnt[slot] = cnt;
     }
-    for (i = 0; i < N_PIPE; i++) CU(cudaStreamSynchronize(g_ctx.stream[i]));
+    for (i = 0; i < N_PIPE; i++) { CU(cudaStreamSynchronize(g_ctx.stream[i])); flush_slot(i); }
+    goto unlock;
 done:
+    for (i = 0; i < N_PIPE; i++) { cudaStreamSynchronize(g_ctx.stream[i]); g_ctx.pend_dst[i] = NULL; }
+unlock:
     pthread_mutex_unlock(&g_lock);
     return rc;
 }

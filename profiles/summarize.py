@@ -23,7 +23,7 @@ rows = [r for r in csv.reader(l for l in open(os.path.join(out, "launches_%s.csv
 hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 with open(os.path.join(ROOT, "profiles", "launches_%s.csv" % tag), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --gib 0.5 --steps 2 --warmup 1\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3 (4 GiB batch)\n")
     f.write("kernel,duration_ns\n")
     tot = {}
     for r in rows[1:]:
