@@ -121,6 +121,59 @@ __device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, u
     if (nIn <= 0) return -1;                                           // lz4.c:2069
     fast = (cap >= 64);                                                // lz4.c:2076
 
+    /* ---- front loop: the fast-loop iterations of lz4.c:2083-2209 that stay in the fast loop ----
+     * Same decisions as the byte-wise code below, but kept to ~60 instructions per sequence: a
+     * thread's time is the latency of its dependent instruction chain (32 threads = 32 different
+     * blocks share a warp, a few warps per SM), so the chain is what is minimised: 32-bit state, two
+     * dependent 4-byte reads per sequence (token + first length byte; offset + first match-length
+     * byte).  Anything that would leave the fast loop (either end of the block getting close, an
+     * error, absurd lengths) exits WITHOUT committing; the exact byte-wise code replays it. */
+    if (fast) {
+        int fip = 0, fop = 0, nextEvt = 0;
+        const int nI = nIn, capI = capIn;
+        while (fip <= nI - 26) {
+            if (fip >= nextEvt) {                                      // checkpoint slot + L1 prefetch, once per 128 input bytes
+                const int slot = fip >> kCkShift;
+                if (ck) {
+                    Checkpoint c; c.tok = kCkEmpty; c.op = 0; c.seq = 0; c.pad = 0;
+                    while (nextSlot < slot) ck[nextSlot++] = c;        // slots no token starts in (slot < kCkSlots: n <= 65535)
+                    c.tok = (uint16_t)fip; c.op = (uint16_t)fop; c.seq = (uint16_t)nseq;
+                    ck[slot] = c;
+                    nextSlot = slot + 1;
+                }
+                if (fip + 128 < nI) prefetch_l1(src + fip + 128);
+                nextEvt = (slot + 1) << kCkShift;
+            }
+            const uint32_t v = ld32u(src + fip);                       // token, then up to 3 bytes that follow it
+            const int mcode = (int)(v & 15u);
+            int lit = (int)((v >> 4) & 15u), q = 1;
+            if (lit == 15) {                                           // read_variable_length (lz4.c:2093), limit n-15
+                uint32_t b = (v >> 8) & 0xFFu;
+                lit += (int)b; q = 2;
+                while (b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { b = ldb(src + fip + q); q++; lit += (int)b; }
+                if (b == 255u || fip + q > nI - 15) break;             // read limit / absurd run: replay byte-wise
+                if ((uint32_t)fop + (uint32_t)lit > (uint32_t)(capI - 32) ||                 // lz4.c:2104 -> safe_literal_copy
+                    (uint32_t)(fip + q) + (uint32_t)lit + 32u > (uint32_t)nI) break;         // (unsigned: sums may pass 2^31)
+            }
+            const int offPos = fip + q + lit;
+            const uint32_t v3 = ld32u(src + offPos);                   // offset (LE16), then the first match-length byte
+            const int off16 = (int)(v3 & 0xFFFFu);
+            int mlen = mcode + kMinMatch, ipn = offPos + 2;
+            if (mcode == 15) {                                         // read_variable_length (lz4.c:2128), limit n-4
+                uint32_t b = (v3 >> 16) & 0xFFu;
+                ipn++; mlen += (int)b;
+                while (b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { b = ldb(src + ipn); ipn++; mlen += (int)b; }
+                if (b == 255u || ipn > nI - 4) break;
+            }
+            const int opn = fop + lit;
+            if ((uint32_t)opn + (uint32_t)mlen >= (uint32_t)(capI - 64)) break;   // lz4.c:2137/2142 -> safe_match_copy
+            if (off16 > opn) { ip = ipn; goto bad; }                   // lz4.c:2161
+            fip = ipn; fop = opn + mlen; nseq++;
+        }
+        ip = fip; op = fop;
+        if (nextEvt > 0) nextPrefetch = (int64_t)nextEvt + 128;
+    }
+
     for (;;) {
         CK_VISIT();
         if (ip + 128 >= nextPrefetch) {                               // keep the input one 128-byte line ahead in L1
