@@ -528,36 +528,50 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
         __syncthreads();
 
         /* ---- phase B: assemble the output in aligned 8-byte chunks ----
-         * Lane L of warp w owns the chunks at w*256 + L*8 + i*(32 warps * 256): at any moment the
-         * CTA works on an 8 KB window that slides forward, so almost all match sources are final
-         * long before they are needed.  The loop is FLATTENED: one iteration handles one PIECE
-         * (literal run or match run clipped to the chunk) per lane -- one unaligned 8-byte read from
-         * the staged input (literals) or the output window (match), masked and shifted into place --
-         * and a lane that finishes its chunk moves on to its next one at once, so lanes with many
-         * small pieces do not stall the others.  A match piece whose source chunks are not flagged
-         * done simply does not advance in this iteration (no spin loops, no warp-level barriers). */
+         * Warp w owns the 256-byte strips w, w+32, w+64, ...: at any moment the CTA works on an
+         * 8 KB window that slides forward, so almost all match sources are final long before they
+         * are needed.  Inside a warp the chunks of its strips are handed out DYNAMICALLY: a lane that
+         * finishes a chunk takes the warp's next one (ballot + popcount ranking), so lanes whose
+         * chunks hold many tiny pieces do not hold the others back.  The loop is flattened: one
+         * iteration handles one PIECE (literal run or match run clipped to the chunk) per lane --
+         * one unaligned 8-byte read from the staged input (literals) or the output window (match),
+         * masked and shifted into place.  A match piece whose source chunks are not flagged done
+         * simply does not advance in this iteration (no spin loops, no warp-level barriers). */
         {
-            const int laneStride = kFastWarps << 8;
-            int p = (warp << 8) + (lane << 3);
-            bool active = p < total;
-            int pe = 0, k = 0, m = 0, e = 0, off = 0, pos = 0;
+            const int nstrips = (total + 255) >> 8;
+            const int warpChunks = (warp < nstrips) ? (((nstrips - 1 - warp) >> 5) + 1) << 5 : 0;   // chunks in this warp's strips
+            int warpNext = 0;                                  // next chunk (of this warp's list) to hand out; warp-uniform
+            bool needNew = true, exhausted = false;
+            int p = 0, pe = 0, k = 0, m = 0, e = 0, off = 0, pos = 0;
             uint32_t d = 0;
             uint64_t acc = 0;
-            #define LOAD_CHUNK()                                                                         \
-                do {                                                                                     \
-                    pe = min(p + 8, total);                                                              \
-                    const uint32_t bw_ = S.bits[p >> 5];                                                 \
-                    k = (int)S.seqbase[p >> 5] + __popc(bw_ & (0xFFFFFFFFu >> (31 - (p & 31)))) - 1;     \
-                    const uint2 r_ = S.rec[k];                                                           \
-                    m = (int)(r_.x & 0xFFFFu); e = (int)(r_.x >> 16); off = (int)(r_.y >> 16);            \
-                    d = r_.y & 0xFFFFu;                                                                  \
-                    if (m == 0 && k != 0) m = 65536;             /* 16-bit wrap of 65536 */              \
-                    if (e == 0) e = 65536;                                                               \
-                    pos = p; acc = 0;                                                                    \
-                } while (0)
-            if (active) LOAD_CHUNK();
-            while (__any_sync(kFull, active)) {
-                if (active) {
+            for (;;) {
+                const unsigned want = __ballot_sync(kFull, needNew && !exhausted);
+                if (want) {
+                    const int c = warpNext + __popc(want & ((1u << lane) - 1u));
+                    warpNext += __popc(want);
+                    if (needNew && !exhausted) {
+                        if (c >= warpChunks) {
+                            exhausted = true;
+                        } else {
+                            p = ((warp + ((c >> 5) << 5)) << 8) + ((c & 31) << 3);
+                            if (p < total) {                   // (chunks past the end of the block are skipped)
+                                pe = min(p + 8, total);
+                                const uint32_t bw = S.bits[p >> 5];
+                                k = (int)S.seqbase[p >> 5] + __popc(bw & (0xFFFFFFFFu >> (31 - (p & 31)))) - 1;
+                                const uint2 r = S.rec[k];
+                                m = (int)(r.x & 0xFFFFu); e = (int)(r.x >> 16); off = (int)(r.y >> 16);
+                                d = r.y & 0xFFFFu;
+                                if (m == 0 && k != 0) m = 65536;   // 16-bit wrap of 65536
+                                if (e == 0) e = 65536;
+                                pos = p; acc = 0;
+                                needNew = false;
+                            }
+                        }
+                    }
+                }
+                if (__ballot_sync(kFull, !needNew) == 0u && __ballot_sync(kFull, !exhausted) == 0u) break;
+                if (!needNew) {
                     bool ok = true;
                     uint64_t v = 0;
                     int end;
@@ -592,13 +606,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                         v &= 0xFFFFFFFFFFFFFFFFull >> (64 - 8 * len);
                         acc |= v << (8 * (pos - p));
                         pos = end;
-                        if (pos >= pe) {                       // chunk complete: publish, take the next one
+                        if (pos >= pe) {                       // chunk complete: publish it
                             *reinterpret_cast<uint64_t*>(S.out + p) = acc;
                             fence_acq_rel_cta();               // data before flag
                             vDone8[p >> 3] = 1;
-                            p += laneStride;
-                            active = p < total;
-                            if (active) LOAD_CHUNK();
+                            needNew = true;
                         } else if (pos == e) {                 // next sequence starts inside this chunk
                             k++;
                             const uint2 r = S.rec[k];
@@ -610,7 +622,6 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                     }
                 }
             }
-            #undef LOAD_CHUNK
         }
         __syncthreads();
         PHASE_MARK(5);                                     // phase B
