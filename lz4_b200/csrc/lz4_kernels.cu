@@ -33,6 +33,7 @@ unsigned long long g_launches = 0;
 
 /* optional phase timing of the fast expand kernel (thread 0 of each CTA; enabled with -DLZ4K_PHASE_TIMING) */
 __device__ unsigned long long g_phaseCycles[8];
+__device__ unsigned long long g_loopStats[4];    // phase B: warp iterations, lane-iterations with a piece, blocked lane-iterations, pieces done
 #ifdef LZ4K_PHASE_TIMING
 #define PHASE_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); atomicAdd(&g_phaseCycles[i], (unsigned long long)(t_ - tPhase)); tPhase = t_; } } while (0)
 #else
@@ -87,31 +88,17 @@ __device__ __forceinline__ bool read_runlength(const uint8_t* src, int64_t& ip, 
     return true;
 }
 
-/* Checkpoint = where the first token at or after input byte 256*j starts: (token position, output
- * position, sequence index).  The expand kernel's lanes restart the token walk from these. */
-struct __align__(8) Checkpoint { uint16_t tok, op, seq, pad; };
-constexpr int kCkShift = 7;
-constexpr int kCkStride = 1 << kCkShift;       // one checkpoint slot per 128 input bytes
-constexpr int kCkSlots = 65536 >> kCkShift;    // enough for inputs <= 65535 bytes
-constexpr uint16_t kCkEmpty = 0xFFFF;
+/* Mark = (token position | output position << 16) of one sequence, written by the scan for every
+ * sequence of a block that may go to the shared-memory expand kernel.  With the marks the expand
+ * kernel rebuilds all sequence records of a block in parallel (one lane per sequence) instead of
+ * re-walking the token chain. */
+constexpr int kMaxSeqFast = 8192;              // record table of the fast expand kernel
+#define MARK_VISIT(tokpos, outpos)                                                              \
+    do { if (marks && nseq < (uint32_t)kMaxSeqFast) marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(outpos) << 16); } while (0)
 
-#define CK_VISIT()                                                                              \
-    do {                                                                                        \
-        if (ck && (ip >> kCkShift) >= nextSlot) {                                               \
-            const int64_t slot = ip >> kCkShift;                                                       \
-            Checkpoint c; c.tok = kCkEmpty; c.op = 0; c.seq = 0; c.pad = 0;                     \
-            while (nextSlot < slot && nextSlot < kCkSlots) ck[nextSlot++] = c;                  \
-            if (slot < kCkSlots && op < 65536 && nseq < 65536) {                                \
-                c.tok = (uint16_t)ip; c.op = (uint16_t)op; c.seq = (uint16_t)nseq;              \
-                ck[slot] = c;                                                                   \
-            }                                                                                   \
-            nextSlot = slot + 1;                                                                \
-        }                                                                                       \
-    } while (0)
-
-__device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut, Checkpoint* ck)
+__device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut, uint32_t* marks)
 {
-    int64_t nextSlot = 0, nextPrefetch = 128;
+    int64_t nextPrefetch = 128;
     int64_t n = nIn, cap = capIn, ip = 0, op = 0, ll = 0, ml = 0, add = 0;
     uint32_t token = 0, offset = 0, nseq = 0;
     bool fast;
@@ -132,18 +119,11 @@ __device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, u
         int fip = 0, fop = 0, nextEvt = 0;
         const int nI = nIn, capI = capIn;
         while (fip <= nI - 26) {
-            if (fip >= nextEvt) {                                      // checkpoint slot + L1 prefetch, once per 128 input bytes
-                const int slot = fip >> kCkShift;
-                if (ck) {
-                    Checkpoint c; c.tok = kCkEmpty; c.op = 0; c.seq = 0; c.pad = 0;
-                    while (nextSlot < slot) ck[nextSlot++] = c;        // slots no token starts in (slot < kCkSlots: n <= 65535)
-                    c.tok = (uint16_t)fip; c.op = (uint16_t)fop; c.seq = (uint16_t)nseq;
-                    ck[slot] = c;
-                    nextSlot = slot + 1;
-                }
+            if (fip >= nextEvt) {                                      // L1 prefetch, once per 128 input bytes
                 if (fip + 128 < nI) prefetch_l1(src + fip + 128);
-                nextEvt = (slot + 1) << kCkShift;
+                nextEvt = ((fip >> 7) + 1) << 7;
             }
+            MARK_VISIT(fip, fop);
             const uint32_t v = ld32u(src + fip);                       // token, then up to 3 bytes that follow it
             const int mcode = (int)(v & 15u);
             int lit = (int)((v >> 4) & 15u), q = 1;
@@ -175,7 +155,7 @@ __device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, u
     }
 
     for (;;) {
-        CK_VISIT();
+        MARK_VISIT(ip, op);
         if (ip + 128 >= nextPrefetch) {                               // keep the input one 128-byte line ahead in L1
             if (ip + 128 < n) prefetch_l1(src + ip + 128);
             nextPrefetch = ip + 256;
@@ -221,11 +201,6 @@ safe_literals:
             if (ip + ll != n || op + ll > cap) goto bad;               // lz4.c:2312
             op += ll; nseq++;
             *nSeqOut = nseq;
-            if (ck) {                                                  // slots no token starts in
-                Checkpoint c; c.tok = kCkEmpty; c.op = 0; c.seq = 0; c.pad = 0;
-                const int64_t lastSlot = (n - 1) >> kCkShift;
-                while (nextSlot <= lastSlot && nextSlot < kCkSlots) ck[nextSlot++] = c;
-            }
             return (int)op;                                            // lz4.c:2439
         }
         ip += ll; op += ll;
@@ -246,12 +221,11 @@ bad:
     return (int)(-ip) - 1;                                             // lz4.c:2443
 }
 
-/* workspace layout (lz4k_decode_workspace_bytes): header | nSeq[N] | fastList[N] | slowList[N] | ckpts[N][256] */
+/* workspace layout (lz4k_decode_workspace_bytes): header | nSeq[N] | fastList[N] | slowList[N] | marks[N][8192] */
 struct WsHeader { uint32_t fastCount, slowCount, fastCursor, pad; };
-constexpr int kMaxSeqFast = 8192;
 
 struct WsView {
-    WsHeader* hdr; uint32_t* nSeq; uint32_t* fastList; uint32_t* slowList; Checkpoint* ck;
+    WsHeader* hdr; uint32_t* nSeq; uint32_t* fastList; uint32_t* slowList; uint32_t* marks;
 };
 __host__ __device__ inline WsView ws_view(void* ws, int64_t n)
 {
@@ -261,7 +235,7 @@ __host__ __device__ inline WsView ws_view(void* ws, int64_t n)
     v.nSeq = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
     v.fastList = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
     v.slowList = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
-    v.ck = reinterpret_cast<Checkpoint*>(p);
+    v.marks = reinterpret_cast<uint32_t*>(p);
     return v;
 }
 
@@ -276,7 +250,7 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
     uint32_t ns = 0;
     /* the smem expand kernel takes blocks whose input and output fit its 64 KB windows */
     const bool maybeFast = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536);
-    int r = scan_block(src, n, cap, &ns, maybeFast ? (w.ck + b * kCkSlots) : nullptr);
+    int r = scan_block(src, n, cap, &ns, maybeFast ? (w.marks + b * kMaxSeqFast) : nullptr);
     a.outSize[b] = r;
     w.nSeq[b] = ns;
     if (r > 0) {
@@ -450,52 +424,41 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
         for (int k = tid; k < 2048; k += kFastThreads) S.bits[k] = 0;
         for (int k = tid; k < 1024; k += kFastThreads) reinterpret_cast<uint64_t*>(S.done8)[k] = 0;
         __syncthreads();
-        /* this lane's checkpoint (phase A), fetched while the TMA load is in flight */
-        const int nslots = (n + kCkStride - 1) >> kCkShift;
-        Checkpoint ckpt; ckpt.tok = kCkEmpty; ckpt.op = 0; ckpt.seq = 0; ckpt.pad = 0;
-        if (tid < nslots) ckpt = w.ck[b * kCkSlots + tid];
-        static_assert(kFastThreads >= kCkSlots, "phase A uses one lane per checkpoint slot");
+        /* this thread's first sequence marks (phase A), fetched while the TMA load is in flight */
+        const uint32_t* marks = w.marks + b * kMaxSeqFast;
+        uint32_t mark0 = 0, mark1 = 0;                         // marks[tid], marks[tid + 1]
+        if (tid < nseq) mark0 = marks[tid];
+        if (tid + 1 < nseq) mark1 = marks[tid + 1];
         PHASE_MARK(0);                                     // fetch + zeroing
         while (!mbar_try_wait(&S.mbar, parity)) { }
         parity ^= 1;
         PHASE_MARK(1);                                     // TMA load wait
 
-        /* ---- phase A: sequence records + start bits ---- */
+        /* ---- phase A: sequence records + start bits, one lane per sequence ----
+         * mark k = (token position, output start) of sequence k; the next mark's output start is where
+         * sequence k ends.  The lane re-reads only its own token: literal length (with extension
+         * bytes), offset; the match length follows from the two output positions. */
         const uint8_t* in = S.in + head;
-        {
-            if (tid < nslots) {
-                const Checkpoint c = ckpt;
-                if (c.tok != kCkEmpty) {
-                    int tok = c.tok, op = c.op, k = c.seq;
-                    const int limit = (tid + 1) * kCkStride;
-                    while (tok < limit) {
-                        const uint32_t t = in[tok];
-                        int p = tok + 1;
-                        int ll = (int)(t >> 4);
-                        if (ll == 15) { uint32_t x; do { x = in[p++]; ll += (int)x; } while (x == 255); }
-                        const int ls = p;
-                        p += ll;
-                        if (op < total) atomicOr(&S.bits[op >> 5], 1u << (op & 31));
-                        const bool last = (p >= n);
-                        uint32_t off = 0;
-                        int ml = 0;
-                        if (!last) {
-                            off = (uint32_t)in[p] | ((uint32_t)in[p + 1] << 8);
-                            p += 2;
-                            ml = (int)(t & 15);
-                            if (ml == 15) { uint32_t x; do { x = in[p++]; ml += (int)x; } while (x == 255); }
-                            ml += kMinMatch;
-                        }
-                        {   /* record: {matchStart | nextStart<<16, (litSrc-outStart)&0xFFFF | offset<<16} */
-                            const uint32_t mstart = (uint32_t)(op + ll);
-                            const uint32_t nxt = last ? (uint32_t)total : (uint32_t)(op + ll + ml);
-                            S.rec[k] = make_uint2((mstart & 0xFFFFu) | (nxt << 16), ((uint32_t)(ls - op) & 0xFFFFu) | (off << 16));
-                        }
-                        if (last) break;
-                        op += ll + ml; tok = p; k++;
-                    }
-                }
-            }
+        for (int k = tid; k < nseq; k += kFastThreads) {
+            const uint32_t mk = (k == tid) ? mark0 : marks[k];
+            const bool last = (k + 1 == nseq);
+            const uint32_t mkn = last ? 0u : ((k == tid) ? mark1 : marks[k + 1]);
+            const int tok = (int)(mk & 0xFFFFu);
+            int op = (int)(mk >> 16);
+            if (k != 0 && op == 0) op = 65536;                 // only an empty final sequence can start at 65536
+            int nxt = last ? total : (int)(mkn >> 16);
+            if (!last && nxt == 0) nxt = 65536;
+            const uint32_t t = in[tok];
+            int pp = tok + 1;
+            int ll = (int)(t >> 4);
+            if (ll == 15) { uint32_t x; do { x = in[pp++]; ll += (int)x; } while (x == 255); }
+            const int ls = pp;                                 // first literal byte in the input
+            uint32_t off = 0;
+            if (!last) off = (uint32_t)in[pp + ll] | ((uint32_t)in[pp + ll + 1] << 8);
+            if (op < total) atomicOr(&S.bits[op >> 5], 1u << (op & 31));
+            /* record: {matchStart | nextStart<<16, (litSrc-outStart)&0xFFFF | offset<<16} */
+            S.rec[k] = make_uint2(((uint32_t)(op + ll) & 0xFFFFu) | ((uint32_t)nxt << 16),
+                                  ((uint32_t)(ls - op) & 0xFFFFu) | (off << 16));
         }
         __syncthreads();
         PHASE_MARK(2);                                     // phase A
@@ -545,6 +508,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
             int p = 0, pe = 0, k = 0, m = 0, e = 0, off = 0, pos = 0;
             uint32_t d = 0;
             uint64_t acc = 0;
+#ifdef LZ4K_PHASE_TIMING
+            unsigned statIter = 0, statLane = 0, statBlocked = 0;
+#endif
             for (;;) {
                 const unsigned want = __ballot_sync(kFull, needNew && !exhausted);
                 if (want) {
@@ -571,6 +537,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                     }
                 }
                 if (__ballot_sync(kFull, !needNew) == 0u && __ballot_sync(kFull, !exhausted) == 0u) break;
+#ifdef LZ4K_PHASE_TIMING
+                statIter++;
+                statLane += __popc(__ballot_sync(kFull, !needNew));
+#endif
                 if (!needNew) {
                     bool ok = true;
                     uint64_t v = 0;
@@ -601,6 +571,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                             }
                         }                                      // off == 0: zero bytes (lz4.c:2407)
                     }
+#ifdef LZ4K_PHASE_TIMING
+                    if (!ok) statBlocked++;
+#endif
                     if (ok) {
                         const int len = end - pos;
                         v &= 0xFFFFFFFFFFFFFFFFull >> (64 - 8 * len);
@@ -622,6 +595,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                     }
                 }
             }
+#ifdef LZ4K_PHASE_TIMING
+            if (lane == 0) { atomicAdd(&g_loopStats[0], (unsigned long long)statIter); atomicAdd(&g_loopStats[1], (unsigned long long)statLane); }
+            atomicAdd(&g_loopStats[2], (unsigned long long)statBlocked);
+#endif
         }
         __syncthreads();
         PHASE_MARK(5);                                     // phase B
@@ -945,11 +922,13 @@ extern "C" {
 uint64_t lz4k_launch_count(void) { return g_launches; }
 
 /* debug: read and reset the phase-cycle counters (all zero unless built with -DLZ4K_PHASE_TIMING) */
-int lz4k_debug_phase_cycles(unsigned long long* out8)
+int lz4k_debug_phase_cycles(unsigned long long* out8)   /* out8: 12 values (8 phase cycles + 4 loop statistics) */
 {
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaError_t e = cudaMemcpyFromSymbol(out8, g_phaseCycles, sizeof(z));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_phaseCycles, z, sizeof(z));
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out8 + 8, g_loopStats, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_loopStats, z, 4 * sizeof(unsigned long long));
     return (int)e;
 }
 
@@ -957,7 +936,7 @@ size_t lz4k_decode_workspace_bytes(int64_t nBlocks)
 {
     if (nBlocks < 0) return 0;
     const size_t lst = (((size_t)nBlocks * 4 + 255) / 256) * 256;
-    return 256 + 3 * lst + (size_t)nBlocks * kCkSlots * sizeof(Checkpoint) + 256;
+    return 256 + 3 * lst + (size_t)nBlocks * kMaxSeqFast * sizeof(uint32_t) + 256;
 }
 
 int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)

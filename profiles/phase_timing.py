@@ -29,7 +29,7 @@ def main():
     for _ in range(3):
         batch.decompress_blocks(packed, offs, sizes, bs, out=out, out_sizes=rets)
     torch.cuda.synchronize()
-    buf = (C.c_ulonglong * 8)()
+    buf = (C.c_ulonglong * 12)()
     raw.LZ4B200_debug_phase_cycles(buf)
     reps = 5
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -41,10 +41,12 @@ def main():
     torch.cuda.synchronize()
     raw.LZ4B200_debug_phase_cycles(buf)
     names = ["fetch+zero", "tma load wait", "phase A", "rank", "prev store wait", "phase B", "store issue", "-"]
-    tot = sum(buf)
+    tot = sum(buf[:8])
     print("expand ms per launch %.3f, blocks %d" % (t0.elapsed_time(t1) / reps, n_blocks))
-    for n, v in zip(names, buf):
+    for n, v in zip(names, buf[:8]):
         print("%-16s %8.0f cycles/block  %5.1f%%" % (n, v / (reps * n_blocks), 100.0 * v / max(tot, 1)))
+    it, la, bl = buf[8] / (reps * n_blocks), buf[9] / (reps * n_blocks), buf[10] / (reps * n_blocks)
+    print("phase B per block: %.0f warp-iterations, %.0f lane-iterations with a piece (%.1f per warp-iteration), %.0f blocked" % (it, la, la / max(it, 1), bl))
     assert torch.equal(out, src)
 
 
