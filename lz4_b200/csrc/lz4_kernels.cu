@@ -4,7 +4,7 @@
  * Decode = two kernels:
  *   scan   : one THREAD per block walks the token chain and applies every acceptance rule of the
  *            reference decoder (lz4.c:2022-2445, x86-64 control flow incl. the fast loop), giving
- *            the exact return value.  No data is moved.
+ *            the exact return value, and leaves a 4-byte mark per sequence.  No data is moved.
  *   expand : moves the bytes of blocks the scan accepted (literal + match copies).
  * Encode = one WARP per block replaying the reference's greedy parse (lz4.c:930-1338) with the
  *   32 lanes probing 32 consecutive search positions per step; output is byte-identical.
@@ -303,18 +303,17 @@ __global__ void __launch_bounds__(128) lz4_expand_generic_kernel(lz4k_decode_arg
  * expand (fast): one CTA per 64 KB block, everything staged in shared memory
  *
  *   TMA bulk load  : compressed block  HBM -> smem            (cp.async.bulk + mbarrier)
- *   phase A        : one LANE per 128-byte input slot restarts the token walk at the scan's
- *                    checkpoint and writes an 8-byte record per sequence + a start-bit per
- *                    sequence (bit index = output position)
+ *   phase A        : one LANE per sequence turns the scan's mark (token position, output position)
+ *                    into an 8-byte record {matchStart, nextStart, litSrc-outStart, offset} and sets
+ *                    a start bit per sequence (bit index = output position)
  *   rank           : exclusive scan of the popcounts of the start bits (sequence index of a byte =
  *                    rank of the last start bit at or before it)
- *   phase B        : one warp per 128-byte strip of output, one aligned 4-byte word per lane: the
- *                    word is assembled from at most four sources (literals/match of the sequence
- *                    covering its first byte and of the next one) read unaligned from smem, and
- *                    stored once.  Match sources that are not final yet are waited for (strip
- *                    frontier across warps, lane frontier inside the strip).
+ *   phase B        : output-major assembly in aligned 8-byte chunks handed out dynamically to the lanes
+ *                    of a warp; one loop iteration = one piece (literal or match run clipped to the
+ *                    chunk) per lane = one unaligned 8-byte smem read, masked and shifted into place;
+ *                    per-chunk done flags order match reads after the writes they depend on.
  *   TMA bulk store : decoded block  smem -> HBM              (cp.async.bulk.global.shared::cta)
- * HBM traffic is exactly the algorithmic bytes (C_i in, U_i out) plus the checkpoints.
+ * HBM traffic is exactly the algorithmic bytes (C_i in, U_i out) plus 4 bytes of marks per sequence.
  * ============================================================================================= */
 #ifndef LZ4K_FAST_THREADS
 #define LZ4K_FAST_THREADS 1024
