@@ -312,3 +312,40 @@ def test_full_size_round_trip_property(lib, oracle):
         eret, eout = oracle.compress(d[i * bs:(i + 1) * bs], 1)
         got = slots[i * stride:i * stride + int(sz[i])].cpu().numpy().tobytes()
         assert sz[i] == eret and got == eout
+
+
+def test_mixed_batch_fast_and_slow_lists(lib, oracle):
+    """One batch mixing everything the two expand kernels see: RLE / periodic / text-like 64 KB blocks
+    (long self-overlapping matches, periods 1..7 and 8..40), P10/P50/P90 datagen, incompressible blocks
+    (compressed size > 65535 -> slow list), short and empty blocks, and a 300 KB block."""
+    from lz4_b200 import batch
+    rng = np.random.default_rng(12)
+    words = [b"alpha", b"beta", b"gamma", b"delta", b"epsilon", b"zeta", b"eta", b"theta", b"iota", b"kappa"]
+    blocks = []
+    blocks.append(np.zeros(65536, dtype=np.uint8).tobytes())
+    for period in (1, 2, 3, 5, 7, 8, 9, 13, 16, 31, 40):
+        pat = bytes(rng.integers(0, 256, period, dtype=np.uint8))
+        blocks.append((pat * (65536 // period + 1))[:65536])
+    blocks.append(b" ".join(words[int(i)] for i in rng.integers(0, len(words), 20000))[:65536])
+    for p, seed in ((0.1, 1), (0.5, 2), (0.9, 3), (0.9, 4), (0.0, 5), (0.0, 6), (1.0, 7)):
+        blocks.append(oracle.datagen(65536, p, seed).tobytes())
+    blocks.append(oracle.datagen(100, 0.5, 8).tobytes())
+    blocks.append(b"")
+    blocks.append(oracle.datagen(12, 0.5, 9).tobytes())
+    blocks.append(oracle.datagen(300000, 0.5, 10).tobytes())
+    blocks.append((b"abcdefgh" * 9000)[:65536 - 7])
+    comp = [oracle.compress(b, 1)[1] for b in blocks]
+    caps = [max(len(b), 1) for b in blocks]
+    res = decode_batch(comp, caps)
+    for b, c, cap, (ret, out) in zip(blocks, comp, caps, res):
+        assert (ret, out) == oracle.decompress(c, cap)
+        assert ret == len(b) and out == b
+    # the same data compressed by the GPU must be byte-identical too (fixed 64 KB blocks only)
+    full = [b for b in blocks if len(b) == 65536]
+    src = to_dev(np.frombuffer(b"".join(full), dtype=np.uint8).copy())
+    slots, sizes, stride = batch.compress_blocks(src, 65536, 1)
+    torch.cuda.synchronize()
+    host = slots.cpu().numpy()
+    for i, (b, n) in enumerate(zip(full, sizes.cpu().numpy())):
+        eret, eout = oracle.compress(b, 1)
+        assert n == eret and host[i * stride:i * stride + n].tobytes() == eout
