@@ -151,6 +151,41 @@ LZ4B200_API int LZ4B200_compress_blocks_host(const void* h_src, int64_t srcStrid
                                              void* h_dst, int64_t dstStride, int32_t dstCap, int acceleration,
                                              int32_t* h_outSize, int64_t nBlocks);
 
+/* ---------------------------------------------------------------------------------------------
+ * 4. Frame layer: one-shot LZ4 frames of INDEPENDENT blocks, host buffers.
+ *    The container logic (header, block headers, EndMark) runs on the host, every block goes through
+ *    the batch layer in one pipeline instead of lz4frame.c's serial per-block loop
+ *    (lz4frame.c:1046-1055 / :1839-1919).
+ * ------------------------------------------------------------------------------------------- */
+#define LZ4B200_ERR_FRAME        (-3)   /* malformed frame (bad magic / header checksum / block size / truncated) */
+#define LZ4B200_ERR_UNSUPPORTED  (-4)   /* valid LZ4 frame feature outside this layer: linked blocks, block or
+                                           content checksums, dictID, skippable frames, HC levels */
+#define LZ4B200_ERR_DSTSIZE      (-5)   /* destination buffer too small */
+
+/* Upper bound of the frame LZ4B200_compressFrame_host can produce (>= LZ4F_compressFrameBound, lz4frame.c:406). */
+LZ4B200_API int64_t LZ4B200_compressFrameBound(int64_t srcSize, int blockSizeID);
+
+/*
+ * LZ4F_compressFrame (lz4frame.h:224 / lz4frame.c:484) for preferences
+ *   { frameInfo = { blockSizeID, LZ4F_blockIndependent, noContentChecksum, LZ4F_frame,
+ *                   contentSize = contentSizeFlag ? srcSize : 0, dictID 0, noBlockChecksum },
+ *     compressionLevel <= 1 (0/1: acceleration 1; negative: acceleration -level+1, lz4frame.c:913) }.
+ * blockSizeID: 0 (default = 4) or 4..7 = 64 KB / 256 KB / 1 MB / 4 MB; shrunk for small inputs exactly like
+ * LZ4F_optimalBSID (lz4frame.c:362-373).  The frame is byte-identical to the reference's.
+ * Returns the frame size, or a negative LZ4B200_ERR_* value.
+ */
+LZ4B200_API int64_t LZ4B200_compressFrame_host(const void* h_src, int64_t srcSize, void* h_dst, int64_t dstCapacity,
+                                               int blockSizeID, int compressionLevel, int contentSizeFlag);
+
+/*
+ * Decode ONE whole frame (the one-shot use of LZ4F_decompress, lz4frame.c:1613): header checks as
+ * LZ4F_decodeHeader (lz4frame.c:1340-1425), then all blocks in one batch (stored-raw blocks are copied).
+ * Returns the number of decoded bytes, or a negative LZ4B200_ERR_* value (LZ4B200_ERR_FRAME also when a
+ * block fails to decode or the content size field disagrees).  *consumed (optional) = frame length.
+ */
+LZ4B200_API int64_t LZ4B200_decompressFrame_host(const void* h_src, int64_t srcSize, void* h_dst, int64_t dstCapacity,
+                                                 int64_t* consumed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -429,3 +429,239 @@ int LZ4_decompress_safe_usingDict(const char* src, char* dst, int compressedSize
     if (dictSize == 0) return LZ4_decompress_safe(src, dst, compressedSize, dstCapacity);   /* lz4.c:2721-2722 */
     return -1;   /* prefix / external dictionaries: SURVEY.md section 8 (f-4), not on the GPU path */
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* frame layer: independent-block LZ4 frames over host buffers          */
+/* ------------------------------------------------------------------------------------------ */
+#define FRAME_MAGIC 0x184D2204u            /* lz4frame.c: LZ4F_MAGICNUMBER */
+#define FRAME_MAGIC_SKIPPABLE 0x184D2A50u  /* .. LZ4F_MAGIC_SKIPPABLE_START */
+
+static uint32_t rd_le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static void wr_le32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+static uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+/* XXH32 of a short message (len < 16), as published in the xxHash specification; the frame header
+ * checksum is its second byte (lz4frame.c:781-809: HC = (XXH32(descriptor, 0) >> 8) & 0xFF). */
+static uint32_t xxh32_short(const uint8_t* p, size_t len, uint32_t seed)
+{
+    const uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+    const uint8_t* end = p + len;
+    uint32_t h = seed + P5 + (uint32_t)len;
+    while (p + 4 <= end) { h += rd_le32(p) * P3; h = rotl32(h, 17) * P4; p += 4; }
+    while (p < end) { h += (uint32_t)(*p) * P5; h = rotl32(h, 11) * P1; p++; }
+    h ^= h >> 15; h *= P2; h ^= h >> 13; h *= P3; h ^= h >> 16;
+    return h;
+}
+
+static int64_t frame_block_bytes(int bsid) { return (int64_t)1 << (8 + 2 * bsid); }   /* 4..7 -> 64 KB..4 MB (lz4frame.c:333-342) */
+
+/* LZ4F_optimalBSID, lz4frame.c:362-373 */
+static int frame_optimal_bsid(int requested, int64_t srcSize)
+{
+    int proposed = 4;
+    int64_t maxBlock = 64 * 1024;
+    while (requested > proposed) {
+        if (srcSize <= maxBlock) return proposed;
+        proposed++;
+        maxBlock <<= 2;
+    }
+    return requested;
+}
+
+int64_t LZ4B200_compressFrameBound(int64_t srcSize, int blockSizeID)
+{
+    int64_t bs, nBlocks;
+    if (srcSize < 0) return LZ4B200_ERR_ARG;
+    if (blockSizeID == 0) blockSizeID = 4;
+    if (blockSizeID < 4 || blockSizeID > 7) return LZ4B200_ERR_ARG;
+    bs = frame_block_bytes(blockSizeID);
+    nBlocks = srcSize / bs + 1;
+    return 19 + nBlocks * 4 + srcSize + 4 + 4;     /* max header + block headers + data + EndMark (+ slack) */
+}
+
+int64_t LZ4B200_compressFrame_host(const void* h_src, int64_t srcSize, void* h_dst, int64_t dstCapacity,
+                                   int blockSizeID, int compressionLevel, int contentSizeFlag)
+{
+    const uint8_t* src = (const uint8_t*)h_src;
+    uint8_t* dst = (uint8_t*)h_dst;
+    int64_t bs, nFull, lastSize, nBlocks, op = 0, first;
+    int accel, bsid;
+    if (srcSize < 0 || (!h_src && srcSize > 0) || !h_dst) return LZ4B200_ERR_ARG;
+    if (blockSizeID == 0) blockSizeID = 4;
+    if (blockSizeID < 4 || blockSizeID > 7) return LZ4B200_ERR_ARG;
+    if (compressionLevel >= 2) return LZ4B200_ERR_UNSUPPORTED;          /* LZ4HC levels (lz4frame.c:952-962) */
+    if (dstCapacity < LZ4B200_compressFrameBound(srcSize, blockSizeID)) return LZ4B200_ERR_DSTSIZE;
+    accel = compressionLevel < 0 ? -compressionLevel + 1 : 1;           /* lz4frame.c:913 */
+    bsid = frame_optimal_bsid(blockSizeID, srcSize);                     /* lz4frame.c:447 */
+    bs = frame_block_bytes(bsid);
+    if (srcSize == 0) contentSizeFlag = 0;                               /* lz4frame.c:445: contentSize = srcSize = 0 -> no field */
+
+    /* frame header, lz4frame.c:781-809 */
+    wr_le32(dst, FRAME_MAGIC); op = 4;
+    dst[op++] = (uint8_t)((1u << 6) | (1u << 5) | ((contentSizeFlag ? 1u : 0u) << 3));   /* version 01, B.Indep */
+    dst[op++] = (uint8_t)((uint32_t)bsid << 4);
+    if (contentSizeFlag) { int i; for (i = 0; i < 8; i++) dst[op++] = (uint8_t)((uint64_t)srcSize >> (8 * i)); }
+    dst[op] = (uint8_t)(xxh32_short(dst + 4, (size_t)(op - 4), 0) >> 8);
+    op++;
+
+    nFull = srcSize / bs;
+    lastSize = srcSize - nFull * bs;
+    nBlocks = nFull + (lastSize > 0);
+    if (nBlocks > 0) {
+        /* blocks go through the batch layer in groups; each block is compressed with dstCapacity = size - 1,
+         * a result of 0 means "store raw" (LZ4F_makeBlock, lz4frame.c:883-908) */
+        const int64_t slotStride = (bs + 15) & ~(int64_t)15;
+        int64_t group = ((int64_t)512 << 20) / bs;
+        uint8_t* slots;
+        int32_t* sizes;
+        if (group < 1) group = 1;
+        if (group > nBlocks) group = nBlocks;
+        slots = (uint8_t*)malloc((size_t)(group * slotStride));
+        sizes = (int32_t*)malloc((size_t)group * sizeof(int32_t));
+        if (!slots || !sizes) { free(slots); free(sizes); return LZ4B200_ERR_ARG; }
+        for (first = 0; first < nBlocks; first += group) {
+            const int64_t cnt = (nBlocks - first < group) ? nBlocks - first : group;
+            const int64_t fullInGroup = (first + cnt > nFull) ? nFull - first : cnt;   /* the ragged block, if any, is the last */
+            int64_t k;
+            int rc = LZ4B200_OK;
+            if (fullInGroup > 0)
+                rc = LZ4B200_compress_blocks_host(src + first * bs, bs, (int32_t)bs, bs, slots, slotStride, (int32_t)(bs - 1),
+                                                  accel, sizes, fullInGroup);
+            if (rc == LZ4B200_OK && fullInGroup < cnt)                    /* final short block: its own capacity */
+                rc = LZ4B200_compress_blocks_host(src + nFull * bs, lastSize, (int32_t)lastSize, lastSize,
+                                                  slots + fullInGroup * slotStride, slotStride, (int32_t)(lastSize - 1),
+                                                  accel, sizes + fullInGroup, 1);
+            if (rc != LZ4B200_OK) { free(slots); free(sizes); return rc; }
+            for (k = 0; k < cnt; k++) {
+                const int64_t blk = first + k;
+                const int64_t sz = (blk < nFull) ? bs : lastSize;
+                const int32_t c = sizes[k];
+                if (c <= 0 || c >= sz) {                                   /* lz4frame.c:896-899 */
+                    wr_le32(dst + op, (uint32_t)sz | 0x80000000u); op += 4;
+                    memcpy(dst + op, src + blk * bs, (size_t)sz); op += sz;
+                } else {
+                    wr_le32(dst + op, (uint32_t)c); op += 4;
+                    memcpy(dst + op, slots + k * slotStride, (size_t)c); op += c;
+                }
+            }
+        }
+        free(slots); free(sizes);
+    }
+    wr_le32(dst + op, 0); op += 4;                                        /* EndMark, lz4frame.c:1222 */
+    return op;
+}
+
+int64_t LZ4B200_decompressFrame_host(const void* h_src, int64_t srcSize, void* h_dst, int64_t dstCapacity,
+                                     int64_t* consumed)
+{
+    const uint8_t* src = (const uint8_t*)h_src;
+    uint8_t* dst = (uint8_t*)h_dst;
+    int64_t ip, bs, nBlocks = 0, capBlocks = 0, k, total = 0, contentSize = -1;
+    int64_t* off = NULL; int32_t* csz = NULL; int32_t* rets = NULL; uint8_t* raw = NULL;
+    int64_t result = LZ4B200_ERR_FRAME;
+    uint32_t flg, bd, hdrLen;
+    int bsid, needCompact = 0;
+    if (!h_src || srcSize < 0 || dstCapacity < 0 || (!h_dst && dstCapacity > 0)) return LZ4B200_ERR_ARG;
+    if (srcSize < 7) return LZ4B200_ERR_FRAME;                            /* minFHSize, lz4frame.h:280 */
+    if ((rd_le32(src) & 0xFFFFFFF0u) == FRAME_MAGIC_SKIPPABLE) return LZ4B200_ERR_UNSUPPORTED;
+    if (rd_le32(src) != FRAME_MAGIC) return LZ4B200_ERR_FRAME;
+    flg = src[4];
+    if (((flg >> 6) & 3) != 1 || ((flg >> 1) & 1)) return LZ4B200_ERR_FRAME;   /* version, reserved bit */
+    hdrLen = 7 + ((flg >> 3) & 1 ? 8 : 0) + ((flg & 1) ? 4 : 0);
+    if (srcSize < hdrLen) return LZ4B200_ERR_FRAME;
+    bd = src[5];
+    bsid = (int)((bd >> 4) & 7);
+    if ((bd >> 7) || (bd & 15) || bsid < 4) return LZ4B200_ERR_FRAME;     /* lz4frame.c:1406-1412 */
+    if ((uint8_t)(xxh32_short(src + 4, hdrLen - 5, 0) >> 8) != src[hdrLen - 1]) return LZ4B200_ERR_FRAME;
+    if (!((flg >> 5) & 1)) return LZ4B200_ERR_UNSUPPORTED;                 /* linked blocks (f-4) */
+    if (((flg >> 4) & 1) || ((flg >> 2) & 1) || (flg & 1)) return LZ4B200_ERR_UNSUPPORTED;   /* checksums (f-3), dictID */
+    if ((flg >> 3) & 1) { int i; uint64_t v = 0; for (i = 0; i < 8; i++) v |= (uint64_t)src[6 + i] << (8 * i); contentSize = (int64_t)v; }
+    bs = frame_block_bytes(bsid);
+
+    /* walk the chain of block headers (serial, O(#blocks)), lz4frame.c:1729-1758 */
+    ip = hdrLen;
+    for (;;) {
+        uint32_t h; int64_t sz;
+        if (ip + 4 > srcSize) goto done;
+        h = rd_le32(src + ip); ip += 4;
+        if (h == 0) break;                                                /* EndMark */
+        sz = (int64_t)(h & 0x7FFFFFFFu);
+        if (sz > bs || ip + sz > srcSize) goto done;                       /* lz4frame.c:1745: maxBlockSize_invalid */
+        if (nBlocks == capBlocks) {
+            capBlocks = capBlocks ? capBlocks * 2 : 1024;
+            off = (int64_t*)realloc(off, (size_t)capBlocks * sizeof(int64_t));
+            csz = (int32_t*)realloc(csz, (size_t)capBlocks * sizeof(int32_t));
+            raw = (uint8_t*)realloc(raw, (size_t)capBlocks);
+            if (!off || !csz || !raw) { result = LZ4B200_ERR_ARG; goto done; }
+        }
+        off[nBlocks] = ip; csz[nBlocks] = (int32_t)sz; raw[nBlocks] = (uint8_t)(h >> 31);
+        nBlocks++;
+        ip += sz;
+    }
+    if (consumed) *consumed = ip;
+    if (nBlocks == 0) { result = (contentSize > 0) ? LZ4B200_ERR_FRAME : 0; goto done; }
+
+    /* Blocks of a one-shot frame are all full except the last, so block i lands at i * blockSize; every
+     * block is decoded with dstCapacity = maxBlockSize like lz4frame.c:1901-1904 does.  All blocks but the
+     * last go straight into h_dst; the last one (and anything irregular) through a bounce buffer. */
+    rets = (int32_t*)malloc((size_t)nBlocks * sizeof(int32_t));
+    if (!rets) { result = LZ4B200_ERR_ARG; goto done; }
+    {
+        const int64_t direct = nBlocks - 1;
+        /* regular frames decode straight into h_dst; a frame with short non-final blocks (a flushed
+         * stream) may need more room than the caller's buffer while its blocks sit at i * blockSize */
+        const int useTemp = (direct * bs > dstCapacity);
+        uint8_t* base = dst;
+        uint8_t* bounce = NULL;
+        uint8_t* temp = NULL;
+        int64_t w = 0;
+        if (useTemp) {
+            temp = (uint8_t*)malloc((size_t)(direct * bs));
+            if (!temp) { result = LZ4B200_ERR_ARG; goto done; }
+            base = temp;
+        }
+        if (direct > 0) {
+            /* stored-raw blocks need no GPU: they enter the batch with size 0 (rejected there) and are copied here */
+            int32_t* tmpSz = (int32_t*)malloc((size_t)direct * sizeof(int32_t));
+            int rc;
+            if (!tmpSz) { free(temp); result = LZ4B200_ERR_ARG; goto done; }
+            for (k = 0; k < direct; k++) tmpSz[k] = raw[k] ? 0 : csz[k];
+            rc = LZ4B200_decompress_blocks_host(src, off, tmpSz, base, bs, (int32_t)bs, rets, direct);
+            free(tmpSz);
+            if (rc != LZ4B200_OK) { free(temp); result = rc; goto done; }
+            for (k = 0; k < direct; k++) {
+                if (raw[k]) { memcpy(base + k * bs, src + off[k], (size_t)csz[k]); rets[k] = csz[k]; }
+                if (rets[k] < 0) { free(temp); goto done; }               /* a block failed to decode */
+                if (rets[k] != bs) needCompact = 1;
+            }
+        }
+        bounce = (uint8_t*)malloc((size_t)bs);
+        if (!bounce) { free(temp); result = LZ4B200_ERR_ARG; goto done; }
+        k = nBlocks - 1;
+        if (raw[k]) { memcpy(bounce, src + off[k], (size_t)csz[k]); rets[k] = csz[k]; }
+        else {
+            int rc = LZ4B200_decompress_blocks_host(src, off + k, csz + k, bounce, bs, (int32_t)bs, rets + k, 1);
+            if (rc != LZ4B200_OK) { free(bounce); free(temp); result = rc; goto done; }
+            if (rets[k] < 0) { free(bounce); free(temp); goto done; }
+        }
+        if (needCompact || useTemp) {                                     /* close the gaps / move out of the temp buffer */
+            for (k = 0; k < direct; k++) {
+                if (w + rets[k] > dstCapacity) { free(bounce); free(temp); result = LZ4B200_ERR_DSTSIZE; goto done; }
+                if (base + k * bs != dst + w) memmove(dst + w, base + k * bs, (size_t)rets[k]);
+                w += rets[k];
+            }
+            total = w;
+        } else {
+            total = direct * bs;
+        }
+        if (total + rets[nBlocks - 1] > dstCapacity) { free(bounce); free(temp); result = LZ4B200_ERR_DSTSIZE; goto done; }
+        memcpy(dst + total, bounce, (size_t)rets[nBlocks - 1]);
+        total += rets[nBlocks - 1];
+        free(bounce); free(temp);
+    }
+    if (contentSize >= 0 && contentSize != total) goto done;              /* lz4frame.c: frameSize_wrong */
+    result = total;
+done:
+    free(off); free(csz); free(raw); free(rets);
+    return result;
+}

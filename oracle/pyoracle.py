@@ -167,6 +167,76 @@ class Reference(_Codec):
             self.lib.RDG_genBuffer(_ptr(buf), int(size), float(proba), float(lit_proba), int(seed))
         return buf
 
+    # --- frame layer (lib/lz4frame.c), used to pin LZ4B200_compressFrame_host / decompressFrame_host ---
+    class _FrameInfo(C.Structure):          # LZ4F_frameInfo_t, lz4frame.h:175-183
+        _fields_ = [("blockSizeID", C.c_int), ("blockMode", C.c_int), ("contentChecksumFlag", C.c_int),
+                    ("frameType", C.c_int), ("contentSize", C.c_ulonglong), ("dictID", C.c_uint),
+                    ("blockChecksumFlag", C.c_int)]
+
+    def have_frame(self):
+        return hasattr(self.lib, "LZ4F_compressFrame")
+
+    def compress_frame(self, data, block_size_id=4, level=0, content_size=False, block_mode=1,
+                       content_checksum=0, block_checksum=0):
+        """LZ4F_compressFrame (lz4frame.c:484) with the given preferences; returns the frame bytes."""
+        lib = self.lib
+        class Prefs(C.Structure):              # LZ4F_preferences_t, lz4frame.h:192-198
+            _fields_ = [("frameInfo", Reference._FrameInfo), ("compressionLevel", C.c_int), ("autoFlush", C.c_uint),
+                        ("favorDecSpeed", C.c_uint), ("reserved", C.c_uint * 3)]
+        p = Prefs()
+        p.frameInfo.blockSizeID = block_size_id
+        p.frameInfo.blockMode = block_mode                 # 1 = LZ4F_blockIndependent
+        p.frameInfo.contentChecksumFlag = content_checksum
+        p.frameInfo.blockChecksumFlag = block_checksum
+        p.frameInfo.contentSize = 1 if content_size else 0   # any non-zero value: replaced by srcSize (lz4frame.c:445)
+        p.compressionLevel = level
+        src = _as_u8(data)
+        lib.LZ4F_compressFrameBound.restype = C.c_size_t
+        lib.LZ4F_compressFrameBound.argtypes = [C.c_size_t, C.c_void_p]
+        lib.LZ4F_compressFrame.restype = C.c_size_t
+        lib.LZ4F_compressFrame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.LZ4F_isError.restype = C.c_uint
+        lib.LZ4F_isError.argtypes = [C.c_size_t]
+        cap = lib.LZ4F_compressFrameBound(len(src), C.byref(p))
+        dst = np.empty(cap, dtype=np.uint8)
+        r = lib.LZ4F_compressFrame(dst.ctypes.data, cap, src.ctypes.data if len(src) else None, len(src), C.byref(p))
+        if lib.LZ4F_isError(r):
+            raise RuntimeError("LZ4F_compressFrame failed")
+        return dst[:r].tobytes()
+
+    def decompress_frame(self, frame, capacity):
+        """LZ4F_decompress (lz4frame.c:1613) of one whole frame; returns the decoded bytes."""
+        lib = self.lib
+        lib.LZ4F_createDecompressionContext.restype = C.c_size_t
+        lib.LZ4F_createDecompressionContext.argtypes = [C.POINTER(C.c_void_p), C.c_uint]
+        lib.LZ4F_freeDecompressionContext.argtypes = [C.c_void_p]
+        lib.LZ4F_decompress.restype = C.c_size_t
+        lib.LZ4F_decompress.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p,
+                                        C.POINTER(C.c_size_t), C.c_void_p]
+        lib.LZ4F_isError.restype = C.c_uint
+        lib.LZ4F_isError.argtypes = [C.c_size_t]
+        ctx = C.c_void_p()
+        assert not lib.LZ4F_isError(lib.LZ4F_createDecompressionContext(C.byref(ctx), 100))
+        src = _as_u8(frame)
+        dst = np.empty(max(int(capacity), 1), dtype=np.uint8)
+        sp, dp = 0, 0
+        try:
+            while sp < len(src):
+                ssz = C.c_size_t(len(src) - sp)
+                dsz = C.c_size_t(int(capacity) - dp)
+                r = lib.LZ4F_decompress(ctx, dst.ctypes.data + dp, C.byref(dsz), src.ctypes.data + sp, C.byref(ssz), None)
+                if lib.LZ4F_isError(r):
+                    raise RuntimeError("LZ4F_decompress failed")
+                sp += ssz.value
+                dp += dsz.value
+                if r == 0:
+                    break
+                if ssz.value == 0 and dsz.value == 0:
+                    raise RuntimeError("LZ4F_decompress made no progress (dst too small?)")
+        finally:
+            lib.LZ4F_freeDecompressionContext(ctx)
+        return dst[:dp].tobytes()
+
 
 def have_reference():
     return os.path.exists(REF_SO)

@@ -124,12 +124,30 @@ def main():
         json.dump({"source": "tests/datagen.c RDG_genBuffer + lib/lz4.c LZ4_compress_fast (v1.10.0)",
                    "buffers": dg, "stream": stream}, f, indent=0)
 
+    # frames made by LZ4F_compressFrame (independent blocks, no checksums): digests + one small frame verbatim
+    frames = []
+    for (n, p, seed, bsid, level, csf) in [(0, 0.5, 0, 4, 0, False), (1, 0.5, 0, 4, 0, True), (1000, 0.5, 1, 4, 0, False),
+                                           (65536, 0.5, 2, 4, 0, False), (65537, 0.5, 3, 4, 0, True), (200000, 0.5, 4, 4, 0, False),
+                                           (200000, 0.5, 4, 7, -3, True), (1 << 20, 0.9, 5, 5, 0, False), (300000, 0.0, 6, 4, 0, False),
+                                           ((4 << 20) + 12345, 0.5, 7, 7, 0, True), (3 << 20, 0.5, 8, 6, -9, False),
+                                           (70000, 1.0, 9, 4, 1, False)]:
+        d = ref.datagen(n, p, seed) if n else np.zeros(0, dtype=np.uint8)
+        f = ref.compress_frame(d, bsid, level, csf)
+        row = {"size": n, "proba": p, "seed": seed, "bsid": bsid, "level": level, "content_size": csf,
+               "frame_size": len(f), "frame_sha256": sha(f), "src_sha256": sha(d)}
+        if len(f) <= 1200:
+            row["frame_hex"] = f.hex()
+        frames.append(row)
+    with open(os.path.join(HERE, "frames.json"), "w") as f:
+        json.dump({"source": "lz4 v1.10.0 lib/lz4frame.c LZ4F_compressFrame (blockIndependent, no checksums)",
+                   "frames": frames}, f, indent=0)
+
     # one whole reference-compressed 64 KB P50 block as a binary fixture (BASELINE config 1)
     d = ref.datagen(65536, 0.5, 0)
     _, c = ref.compress(d, 1)
     with open(os.path.join(HERE, "p50_seed0_64k.lz4block"), "wb") as f:
         f.write(c)
-    print("decode cases", len(decode), "compress cases", len(comp), "datagen rows", len(dg), "block", len(c))
+    print("decode cases", len(decode), "compress cases", len(comp), "datagen rows", len(dg), "block", len(c), "frames", len(frames))
 
 
 if __name__ == "__main__":
