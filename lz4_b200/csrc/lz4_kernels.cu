@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(128) lz4_expand_generic_kernel(lz4k_decode_arg
 #endif
 constexpr int kFastThreads = LZ4K_FAST_THREADS;
 constexpr int kFastWarps = kFastThreads / 32;
+static_assert(kFastWarps == 32, "phase B's strip ownership (warp w owns strips w, w+32, ...) assumes 32 warps per CTA");
 constexpr int kInBytes = 65536 + 64;
 
 struct FastSmem {
