@@ -132,3 +132,61 @@ def test_gpu_frame_irregular_and_rejected_inputs(oracle):
     with pytest.raises(Lz4FrameError) as e:
         frame.compress_frame(d, 4, 3, False)                             # LZ4HC level
     assert e.value.code == -4
+
+
+# ------------------------------------------------------------------------------------------
+# host logic of the frame layer that needs no GPU: header validation, error codes, empty frames
+# ------------------------------------------------------------------------------------------
+def _frame_lib():
+    from lz4_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def _decode_rc(lib, frame_bytes, cap=64):
+    import ctypes as C
+    src = np.frombuffer(bytes(frame_bytes), dtype=np.uint8)
+    dst = np.zeros(max(cap, 1), dtype=np.uint8)
+    used = C.c_int64(-1)
+    return int(lib.LZ4B200_decompressFrame_host(src.ctypes.data, len(src), dst.ctypes.data, cap, C.byref(used))), used.value
+
+
+def test_frame_header_validation_needs_no_gpu(oracle):
+    lib = _frame_lib()
+    empty = fo.compress_frame(oracle, b"", 4, 0, False)                   # header + EndMark (lz4frame.c:1222)
+    assert _decode_rc(lib, empty) == (0, len(empty))
+    assert _decode_rc(lib, empty + b"trailing")[0] == 0                    # bytes after the frame are not consumed
+    assert _decode_rc(lib, empty[:6])[0] == -3                             # shorter than minFHSize
+    assert _decode_rc(lib, b"\x05" + empty[1:])[0] == -3                   # magic
+    assert _decode_rc(lib, empty[:6] + bytes([empty[6] ^ 0xFF]) + empty[7:])[0] == -3     # header checksum
+    assert _decode_rc(lib, empty[:7])[0] == -3                             # no EndMark
+    assert _decode_rc(lib, struct.pack("<I", 0x184D2A50) + b"\x04\x00\x00\x00abcd")[0] == -4   # skippable frame
+    for flg, bd, want in (((1 << 6), 4 << 4, -4),                          # linked blocks
+                          ((1 << 6) | (1 << 5) | (1 << 2), 4 << 4, -4),    # content checksum
+                          ((1 << 6) | (1 << 5) | (1 << 4), 4 << 4, -4),    # block checksum
+                          ((2 << 6) | (1 << 5), 4 << 4, -3),               # version
+                          ((1 << 6) | (1 << 5) | 2, 4 << 4, -3),           # reserved FLG bit
+                          ((1 << 6) | (1 << 5), 3 << 4, -3),               # block size id < 4 (lz4frame.c:1409)
+                          ((1 << 6) | (1 << 5), (4 << 4) | 1, -3)):        # reserved BD bits
+        dsc = bytes([flg, bd])
+        fr = struct.pack("<I", 0x184D2204) + dsc + bytes([(fo.xxh32_short(dsc) >> 8) & 0xFF]) + struct.pack("<I", 0)
+        assert _decode_rc(lib, fr)[0] == want, (flg, bd)
+    # a block header announcing more than the maximum block size (lz4frame.c:1745)
+    dsc = bytes([(1 << 6) | (1 << 5), 4 << 4])
+    fr = struct.pack("<I", 0x184D2204) + dsc + bytes([(fo.xxh32_short(dsc) >> 8) & 0xFF]) + struct.pack("<I", 65537) + b"\0" * 65537
+    assert _decode_rc(lib, fr)[0] == -3
+
+
+def test_frame_compress_argument_rules_need_no_gpu():
+    lib = _frame_lib()
+    assert lib.LZ4B200_compressFrameBound(0, 0) == 19 + 4 + 4 + 4
+    assert lib.LZ4B200_compressFrameBound(65536, 4) >= 7 + 4 + 65536 + 4
+    assert lib.LZ4B200_compressFrameBound(100, 3) == -1 and lib.LZ4B200_compressFrameBound(-1, 4) == -1
+    src = np.zeros(100, dtype=np.uint8)
+    dst = np.zeros(4096, dtype=np.uint8)
+    assert lib.LZ4B200_compressFrame_host(src.ctypes.data, 100, dst.ctypes.data, 4096, 4, 2, 0) == -4    # LZ4HC level
+    assert lib.LZ4B200_compressFrame_host(src.ctypes.data, 100, dst.ctypes.data, 50, 4, 0, 0) == -5     # dst too small
+    assert lib.LZ4B200_compressFrame_host(src.ctypes.data, 100, dst.ctypes.data, 4096, 9, 0, 0) == -1    # block size id
+    # an empty input needs no block and therefore no GPU: header + EndMark, content-size flag dropped (lz4frame.c:445)
+    r = lib.LZ4B200_compressFrame_host(None, 0, dst.ctypes.data, 4096, 4, 0, 1)
+    assert r == 11 and dst[:11].tobytes().hex() == "04224d1860408200000000"
