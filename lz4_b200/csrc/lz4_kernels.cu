@@ -536,10 +536,14 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                         }
                     }
                 }
-                if (__ballot_sync(kFull, !needNew) == 0u && __ballot_sync(kFull, !exhausted) == 0u) break;
+                const unsigned act = __ballot_sync(kFull, !needNew);   // lanes holding a chunk
+                if (act == 0u) {
+                    if (__ballot_sync(kFull, !exhausted) == 0u) break;     // nothing in flight, nothing left to hand out
+                    continue;
+                }
 #ifdef LZ4K_PHASE_TIMING
                 statIter++;
-                statLane += __popc(__ballot_sync(kFull, !needNew));
+                statLane += __popc(act);
 #endif
                 if (!needNew) {
                     bool ok = true;
@@ -571,6 +575,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
                             }
                         }                                      // off == 0: zero bytes (lz4.c:2407)
                     }
+                    __syncwarp(act);                           // literal and match lanes rejoin: the tail below runs once
 #ifdef LZ4K_PHASE_TIMING
                     if (!ok) statBlocked++;
 #endif
