@@ -14,6 +14,12 @@
  *
  * There is no CPU fallback: without a usable CUDA device every codec entry point fails
  * (compress -> 0, decompress -> negative, batch -> LZ4B200_ERR_CUDA).
+ *
+ * Threads and devices: every entry point is re-entrant (the host-pointer calls share one context
+ * behind a mutex).  The host-pointer calls (layers 1, 3, 4) run on the CUDA device that is current
+ * in the calling thread at their FIRST use in the process; the device-pointer calls (layer 2) run
+ * on the current device / the given stream, and calls that overlap in time must use different
+ * workspaces.
  */
 #ifndef LZ4_B200_H
 #define LZ4_B200_H
