@@ -1,6 +1,6 @@
 """BASELINE config 4 shape on one GPU: one LZ4 frame of 4 MB independent blocks through the frame layer
 (host buffers): compress, check against the reference's LZ4F_compressFrame digest when available, decompress.
-Usage (under gpurun): python profiles/frame_bench.py [GiB] [blockSizeID]"""
+Usage (under gpurun): python tests/perf/frame_bench.py [GiB] [blockSizeID]"""
 import hashlib
 import json
 import os
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from lz4_b200 import frame  # noqa: E402
 from oracle.pyoracle import Oracle, Reference, have_reference  # noqa: E402

@@ -1,11 +1,11 @@
 """Developer tool: per-phase cycle breakdown of the fast expand kernel.
-Build with LZ4K_PHASE_TIMING=1 (python profiles/phase_timing.py --build), run under gpurun."""
+Build with LZ4K_PHASE_TIMING=1 (python tests/perf/phase_timing.py --build), run under gpurun."""
 import ctypes as C
 import os
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -1,7 +1,7 @@
 """BASELINE.json configs 3 and 5 in one run: compress accel 1/8/32 sweep (ratio + GB/s) and the matching
 decode rate on datagen P50 and P90, 64 KB blocks, next to the CPU reference (all host threads and 1 thread).
 Every GPU-compressed sample block is checked byte-for-byte against the oracle.  Writes one JSON line per row.
-Usage (under gpurun):  python profiles/sweep_configs.py [GiB] > gpurun_out/sweep.jsonl"""
+Usage (under gpurun):  python tests/perf/sweep_configs.py [GiB] > gpurun_out/sweep.jsonl"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from lz4_b200 import batch  # noqa: E402
 from oracle.pyoracle import Oracle, Reference, have_reference  # noqa: E402
