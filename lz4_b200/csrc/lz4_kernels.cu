@@ -31,6 +31,10 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 unsigned long long g_launches = 0;
 
+#ifdef LZ4K_PHASEB_V2
+#include "lz4_phaseb_v2.h"     /* experimental phase B ("uniform body"); not in the default build */
+#endif
+
 /* optional phase timing of the fast expand kernel (thread 0 of each CTA; enabled with -DLZ4K_PHASE_TIMING) */
 __device__ unsigned long long g_phaseCycles[8];
 __device__ unsigned long long g_loopStats[4];    // phase B: warp iterations, lane-iterations with a piece, blocked lane-iterations, pieces done
@@ -334,7 +338,11 @@ struct FastSmem {
     uint32_t warpSum[32];
     alignas(8) uint64_t mbar;
     uint32_t nextIdx[2];                            // work-list cursor values, fetched one block ahead
+#ifdef LZ4K_PHASEB_V2
+    alignas(16) uint8_t done8[8192 + 16];           // + the always-set sentinel flag done8[kPbSentinel]
+#else
     alignas(16) uint8_t done8[8192];                // done8[c] != 0: output bytes [8c, 8c+8) are final
+#endif
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -395,6 +403,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
     volatile uint8_t* vDone8 = S.done8;
 
     if (tid == 0) mbar_init(&S.mbar, 1);
+#ifdef LZ4K_PHASEB_V2
+    if (tid == 0) S.done8[kPbSentinel] = 1;
+#endif
     __syncthreads();
 #ifdef LZ4K_PHASE_TIMING
     long long tPhase = clock64();
@@ -500,6 +511,33 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
          * one unaligned 8-byte read from the staged input (literals) or the output window (match),
          * masked and shifted into place.  A match piece whose source chunks are not flagged done
          * simply does not advance in this iteration (no spin loops, no warp-level barriers). */
+#ifdef LZ4K_PHASEB_V2
+        {   /* experimental: same hand-out and flag protocol, one code path for literal and match pieces */
+            const int nstrips = (total + 255) >> 8;
+            const int warpChunks = (warp < nstrips) ? (((nstrips - 1 - warp) >> 5) + 1) << 5 : 0;
+            int warpNext = 0;
+            PBView V;
+            V.window = S.in; V.out = S.out; V.outDelta = (int)(S.out - S.in);
+            V.rec = reinterpret_cast<const pb_rec*>(S.rec); V.bits = S.bits; V.seqbase = S.seqbase;
+            V.done8 = S.done8; V.head = head; V.total = total;
+            PBLane L;
+            pb_init(L);
+            for (;;) {
+                const unsigned want = __ballot_sync(kFull, L.needNew && !L.exhausted);
+                if (want) {
+                    const int c = warpNext + __popc(want & ((1u << lane) - 1u));
+                    warpNext += __popc(want);
+                    if (L.needNew && !L.exhausted) pb_take(L, V, warp, c, warpChunks);
+                }
+                const unsigned act = __ballot_sync(kFull, !L.needNew);
+                if (act == 0u) {
+                    if (__ballot_sync(kFull, !L.exhausted) == 0u) break;
+                    continue;
+                }
+                if (!L.needNew) pb_body(L, V);
+            }
+        }
+#else
         {
             const int nstrips = (total + 255) >> 8;
             const int warpChunks = (warp < nstrips) ? (((nstrips - 1 - warp) >> 5) + 1) << 5 : 0;   // chunks in this warp's strips
@@ -605,6 +643,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
             atomicAdd(&g_loopStats[2], (unsigned long long)statBlocked);
 #endif
         }
+#endif  /* LZ4K_PHASEB_V2 */
         __syncthreads();
         PHASE_MARK(5);                                     // phase B
 
