@@ -44,21 +44,11 @@ __device__ unsigned long long g_loopStats[4];    // phase B: warp iterations, la
 #define PHASE_MARK(i) do { } while (0)
 #endif
 
-__device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return __ldg(p); }
-__device__ __forceinline__ void prefetch_l1(const uint8_t* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return __ldg(p) | (__ldg(p + 1) << 8); }
+/* byte readers + the per-block scan (scan_front / scan_tail / scan_block): shared with the CPU
+ * emulators under tests/emul/, see the header */
+#define LZ4_SCAN_CORE_CONSTANTS
+#include "lz4_scan_core.h"
 
-/* unaligned little-endian 32-bit read through two aligned words (never touches a word that holds
- * no requested byte) */
-__device__ __forceinline__ uint32_t ld32u(const uint8_t* p)
-{
-    uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-    uint32_t sh = (uint32_t)(a & 3) * 8;
-    uint32_t lo = __ldg(w);
-    uint32_t hi = sh ? __ldg(w + 1) : 0u;
-    return __funnelshift_r(lo, hi, sh);
-}
 /* low 5 bytes at p (for the 5-byte hash, lz4.c:785-791) */
 __device__ __forceinline__ uint64_t ld40u(const uint8_t* p)
 {
@@ -70,159 +60,6 @@ __device__ __forceinline__ uint64_t ld40u(const uint8_t* p)
     uint32_t v = __funnelshift_r(lo, hi, sh);
     uint32_t b4 = (hi >> sh) & 0xFFu;
     return (uint64_t)v | ((uint64_t)b4 << 32);
-}
-
-/* =============================================================================================
- * scan: exact acceptance + return value of LZ4_decompress_safe, one thread per block
- * ============================================================================================= */
-
-/* lz4.c:1978-2014.  ip advances exactly like the reference's pointer so that the error code
- * -(ip)-1 (lz4.c:2443) is reproduced. */
-__device__ __forceinline__ bool read_runlength(const uint8_t* src, int64_t& ip, int64_t ilimit, bool initialCheck, int64_t& total)
-{
-    total = 0;
-    if (initialCheck && ip >= ilimit) return false;
-    uint32_t b;
-    do {
-        b = ldb(src + ip);
-        ip++;
-        total += b;
-        if (ip > ilimit) return false;
-    } while (b == 255);
-    return true;
-}
-
-/* Mark = (token position | output position << 16) of one sequence, written by the scan for every
- * sequence of a block that may go to the shared-memory expand kernel.  With the marks the expand
- * kernel rebuilds all sequence records of a block in parallel (one lane per sequence) instead of
- * re-walking the token chain. */
-constexpr int kMaxSeqFast = 8192;              // record table of the fast expand kernel
-#define MARK_VISIT(tokpos, outpos)                                                              \
-    do { if (marks && nseq < (uint32_t)kMaxSeqFast) marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(outpos) << 16); } while (0)
-
-__device__ int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut, uint32_t* marks)
-{
-    int64_t nextPrefetch = 128;
-    int64_t n = nIn, cap = capIn, ip = 0, op = 0, ll = 0, ml = 0, add = 0;
-    uint32_t token = 0, offset = 0, nseq = 0;
-    bool fast;
-
-    if (capIn < 0) return -1;                                          // lz4.c:2036
-    if (capIn == 0) return (nIn == 1 && ldb(src) == 0) ? 0 : -1;       // lz4.c:2064-2068
-    if (nIn <= 0) return -1;                                           // lz4.c:2069
-    fast = (cap >= 64);                                                // lz4.c:2076
-
-    /* ---- front loop: the fast-loop iterations of lz4.c:2083-2209 that stay in the fast loop ----
-     * Same decisions as the byte-wise code below, but kept to ~60 instructions per sequence: a
-     * thread's time is the latency of its dependent instruction chain (32 threads = 32 different
-     * blocks share a warp, a few warps per SM), so the chain is what is minimised: 32-bit state, two
-     * dependent 4-byte reads per sequence (token + first length byte; offset + first match-length
-     * byte).  Anything that would leave the fast loop (either end of the block getting close, an
-     * error, absurd lengths) exits WITHOUT committing; the exact byte-wise code replays it. */
-    if (fast) {
-        int fip = 0, fop = 0, nextEvt = 0;
-        const int nI = nIn, capI = capIn;
-        while (fip <= nI - 26) {
-            if (fip >= nextEvt) {                                      // L1 prefetch, once per 128 input bytes
-                if (fip + 128 < nI) prefetch_l1(src + fip + 128);
-                nextEvt = ((fip >> 7) + 1) << 7;
-            }
-            MARK_VISIT(fip, fop);
-            const uint32_t v = ld32u(src + fip);                       // token, then up to 3 bytes that follow it
-            const int mcode = (int)(v & 15u);
-            int lit = (int)((v >> 4) & 15u), q = 1;
-            if (lit == 15) {                                           // read_variable_length (lz4.c:2093), limit n-15
-                uint32_t b = (v >> 8) & 0xFFu;
-                lit += (int)b; q = 2;
-                while (b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { b = ldb(src + fip + q); q++; lit += (int)b; }
-                if (b == 255u || fip + q > nI - 15) break;             // read limit / absurd run: replay byte-wise
-                if ((uint32_t)fop + (uint32_t)lit > (uint32_t)(capI - 32) ||                 // lz4.c:2104 -> safe_literal_copy
-                    (uint32_t)(fip + q) + (uint32_t)lit + 32u > (uint32_t)nI) break;         // (unsigned: sums may pass 2^31)
-            }
-            const int offPos = fip + q + lit;
-            const uint32_t v3 = ld32u(src + offPos);                   // offset (LE16), then the first match-length byte
-            const int off16 = (int)(v3 & 0xFFFFu);
-            int mlen = mcode + kMinMatch, ipn = offPos + 2;
-            if (mcode == 15) {                                         // read_variable_length (lz4.c:2128), limit n-4
-                uint32_t b = (v3 >> 16) & 0xFFu;
-                ipn++; mlen += (int)b;
-                while (b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { b = ldb(src + ipn); ipn++; mlen += (int)b; }
-                if (b == 255u || ipn > nI - 4) break;
-            }
-            const int opn = fop + lit;
-            if ((uint32_t)opn + (uint32_t)mlen >= (uint32_t)(capI - 64)) break;   // lz4.c:2137/2142 -> safe_match_copy
-            if (off16 > opn) { ip = ipn; goto bad; }                   // lz4.c:2161
-            fip = ipn; fop = opn + mlen; nseq++;
-        }
-        ip = fip; op = fop;
-        if (nextEvt > 0) nextPrefetch = (int64_t)nextEvt + 128;
-    }
-
-    for (;;) {
-        MARK_VISIT(ip, op);
-        if (ip + 128 >= nextPrefetch) {                               // keep the input one 128-byte line ahead in L1
-            if (ip + 128 < n) prefetch_l1(src + ip + 128);
-            nextPrefetch = ip + 256;
-        }
-        token = ldb(src + ip); ip++;
-        ll = token >> 4;
-        ml = token & 15;
-
-        if (fast) {                                                    // lz4.c:2083-2209
-            if (ll == 15) {
-                if (!read_runlength(src, ip, n - 15, true, add)) goto bad;
-                ll += add;
-                if (op + ll > cap - 32 || ip + ll > n - 32) { fast = false; goto safe_literals; }
-            } else if (ip > n - 17) {
-                fast = false; goto safe_literals;
-            }
-            ip += ll; op += ll;
-            offset = ld16(src + ip); ip += 2;
-            if (ml == 15) {
-                if (!read_runlength(src, ip, n - 4, false, add)) goto bad;
-                ml += add;
-            }
-            ml += kMinMatch;
-            if (op + ml >= cap - 64) { fast = false; goto safe_match; }
-            if ((int64_t)offset > op) goto bad;                        // lz4.c:2161
-            op += ml; nseq++;
-            continue;
-        }
-
-        /* safe loop, lz4.c:2215-2435 */
-        if (ll != 15 && ip < n - 16 && op <= cap - 32) {               // two-stage shortcut :2230-2261
-            op += ll; ip += ll;
-            offset = ld16(src + ip); ip += 2;
-            if (ml != 15 && offset >= 8 && (int64_t)offset <= op) { op += ml + kMinMatch; nseq++; continue; }
-            goto match_length;
-        }
-        if (ll == 15) {
-            if (!read_runlength(src, ip, n - 15, true, add)) goto bad;
-            ll += add;
-        }
-safe_literals:
-        if (op + ll > cap - kMfLimit || ip + ll > n - (2 + 1 + kLastLiterals)) {   // lz4.c:2279
-            if (ip + ll != n || op + ll > cap) goto bad;               // lz4.c:2312
-            op += ll; nseq++;
-            *nSeqOut = nseq;
-            return (int)op;                                            // lz4.c:2439
-        }
-        ip += ll; op += ll;
-        offset = ld16(src + ip); ip += 2;
-match_length:
-        if (ml == 15) {
-            if (!read_runlength(src, ip, n - 4, false, add)) goto bad;
-            ml += add;
-        }
-        ml += kMinMatch;
-safe_match:
-        if ((int64_t)offset > op) goto bad;                            // lz4.c:2356
-        if (op + ml > cap - kLastLiterals) goto bad;                   // lz4.c:2421-2423
-        op += ml; nseq++;
-    }
-bad:
-    *nSeqOut = 0;
-    return (int)(-ip) - 1;                                             // lz4.c:2443
 }
 
 /* workspace layout (lz4k_decode_workspace_bytes): header | nSeq[N] | fastList[N] | slowList[N] | marks[N][8192] */
