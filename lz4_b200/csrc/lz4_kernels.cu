@@ -100,6 +100,57 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
     }
 }
 
+#ifdef LZ4K_SCAN_V2
+/* experimental: one WARP per block (lz4_scan_v2.h); same outputs as lz4_scan_kernel */
+#include "lz4_scan_v2.h"
+__global__ void __launch_bounds__(128) lz4_scan_v2_kernel(lz4k_decode_args a)
+{
+    __shared__ SV2Shared sh[4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * 4 + wib;
+    if (b >= a.nBlocks) return;                                       // whole warp
+    WsView w = ws_view(a.workspace, a.nBlocks);
+    const uint8_t* src = a.src + a.srcOff[b];
+    const int n = a.srcSize[b];
+    const int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
+    const bool maybeFast = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536);
+    uint32_t* marks = maybeFast ? (w.marks + b * kMaxSeqFast) : nullptr;
+    SV2Shared& S = sh[wib];
+    int r = 0;
+    uint32_t ns = 0;
+    if (cap < 64 || n < kSv2MinBytes) {
+        if (lane == 0) r = scan_block(src, n, cap, &ns, marks);
+    } else {
+        SV2Lane L;
+        sv2_phase0(lane, L, S, src, n, cap);
+        __syncwarp();
+        for (;;) {
+            sv2_decide(lane, L, S);
+            if (lane == 0) S.changed = 0;
+            __syncwarp();
+            sv2_redo(lane, L, S, src, n, cap);
+            __syncwarp();
+            const int ch = S.changed;
+            __syncwarp();
+            if (!ch) break;
+        }
+        sv2_write(lane, L, S, src, n, cap, marks);
+        __syncwarp();
+        sv2_finish(lane, S, src, n, cap, marks);
+        __syncwarp();
+        r = S.ret; ns = S.nseq;
+    }
+    if (lane == 0) {
+        a.outSize[b] = r;
+        w.nSeq[b] = ns;
+        if (r > 0) {
+            if (maybeFast && ns <= kMaxSeqFast) w.fastList[atomicAdd(&w.hdr->fastCount, 1u)] = (uint32_t)b;
+            else w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
+        }
+    }
+}
+#endif
+
 /* =============================================================================================
  * expand (generic): one warp per accepted block, any block size, straight to global memory
  * ============================================================================================= */
@@ -831,9 +882,14 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
     if (phases & 1) {
         cudaError_t e = cudaMemsetAsync(a->workspace, 0, 256, s);     // WsHeader: list counters
         if (e != cudaSuccess) return (int)e;
+#ifdef LZ4K_SCAN_V2
+        const int64_t grid = (a->nBlocks + 3) / 4;                    // 4 warps = 4 blocks per CTA
+        lz4_scan_v2_kernel<<<(unsigned)grid, 128, 0, s>>>(*a);
+#else
         const int threads = 128;
         const int64_t grid = (a->nBlocks + threads - 1) / threads;
         lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
+#endif
         g_launches++;
     }
     if (phases & 2) {

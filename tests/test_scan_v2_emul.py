@@ -1,0 +1,125 @@
+"""CPU check of the experimental warp-per-block scan (lz4_b200/csrc/lz4_scan_v2.h, not in the default build).
+
+The header is compiled for the host and its 32 lanes are run phase by phase (tests/emul/scan_v2_emul.cpp);
+for every block -- valid, corrupted, capacity-limited, 64 KB to 4 MB -- the result must be IDENTICAL to
+the one-thread scan of lz4_scan_core.h (itself pinned to the golden vectors and the oracle by
+tests/test_scan_core_host.py): return value, sequence count, and the marks of every sequence.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import Oracle, Reference, have_reference
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_SEQ = 8192
+
+
+@pytest.fixture(scope="module")
+def libs(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    d = tmp_path_factory.mktemp("scanv2")
+    out = []
+    for name in ("scan_emul", "scan_v2_emul"):
+        so = str(d / ("lib%s.so" % name))
+        subprocess.run([gxx, "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", so,
+                        os.path.join(HERE, "emul", name + ".cpp")], check=True)
+        out.append(C.CDLL(so))
+    one, v2 = out
+    one.scan_host.restype = C.c_int
+    one.scan_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
+    v2.scan_v2_host.restype = C.c_int
+    v2.scan_v2_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_int)]
+    return one, v2
+
+
+def both(libs, block, cap, shift=0, with_marks=True):
+    one, v2 = libs
+    n = len(block)
+    buf = np.full(n + 32, 0xEE, dtype=np.uint8)
+    base = buf.ctypes.data
+    pad = (-base) % 8 + 8 + shift
+    buf[pad:pad + n] = np.frombuffer(bytes(block), dtype=np.uint8)
+    m1 = np.full(MAX_SEQ, 0xABABABAB, dtype=np.uint32)
+    m2 = np.full(MAX_SEQ, 0xABABABAB, dtype=np.uint32)
+    n1, n2 = C.c_uint32(0), C.c_uint32(0)
+    stats = (C.c_int * 3)()
+    r1 = one.scan_host(base + pad, n, cap, C.byref(n1), m1.ctypes.data if with_marks else None)
+    r2 = v2.scan_v2_host(base + pad, n, cap, C.byref(n2), m2.ctypes.data if with_marks else None, stats)
+    k = min(n1.value, MAX_SEQ)
+    return (r1, n1.value, m1[:k]), (r2, n2.value, m2[:k]), list(stats)
+
+
+def corrupt(rng, comp):
+    b = bytearray(comp)
+    for _ in range(int(rng.integers(1, 4))):
+        mode = int(rng.integers(0, 4))
+        pos = int(rng.integers(0, max(len(b), 1)))
+        if mode == 0 and b:
+            b[pos] = int(rng.integers(0, 256))
+        elif mode == 1 and b:
+            b[pos] = int(rng.choice([0, 0xFF, 0xF0, 0x0F, 0x10, 0x1F]))
+        elif mode == 2 and len(b) > 4:
+            del b[pos:pos + int(rng.integers(1, 4))]
+        else:
+            b[pos:pos] = bytes(rng.integers(0, 256, int(rng.integers(1, 4)), dtype=np.uint8))
+    return bytes(b)
+
+
+def test_warp_scan_equals_one_thread_scan(libs):
+    orc = Oracle()
+    gen = Reference() if have_reference() else orc
+    rng = np.random.default_rng(20260924)
+    checked = errors = rounds = 0
+    for proba in (0.0, 0.2, 0.5, 0.9, 0.99, 1.0):
+        for size in (2000, 4096, 10000, 65536, 65536, 70000, 300000, 1 << 20, 4 << 20):
+            raw = bytes(gen.datagen(size, proba, int(rng.integers(0, 1 << 30))))
+            _, comp = orc.compress(raw, 1)
+            comp = bytes(comp)
+            caps = {size, size + 1, size + 64, size + 1000, size - 1, size - 70, size // 2, 64, 63}
+            for cap in caps:
+                a, b, st = both(libs, comp, cap, shift=int(rng.integers(0, 4)), with_marks=(len(comp) <= 65535 and cap <= 65536))
+                assert a[0] == b[0] and a[1] == b[1], (proba, size, cap, a[:2], b[:2], st)
+                assert np.array_equal(a[2], b[2]), (proba, size, cap, st)
+                if cap == size:
+                    assert a[0] == size
+                    assert st[0] <= 32                     # the fix-up converges within one round per lane
+                    if proba == 0.5 and size >= 65536:
+                        rounds = max(rounds, st[0])
+                checked += 1
+            for _ in range(10 if size <= 70000 else 3):
+                bad = corrupt(rng, comp)
+                cap = int(rng.choice([size, size + 64, size + 1000, max(size - 5, 0)]))
+                a, b, st = both(libs, bad, cap, shift=int(rng.integers(0, 4)), with_marks=(len(bad) <= 65535 and cap <= 65536))
+                assert a[0] == b[0] and a[1] == b[1], (proba, size, cap, a[:2], b[:2], st)
+                assert np.array_equal(a[2], b[2])
+                errors += a[0] < 0
+                checked += 1
+    assert checked > 800 and errors > 100
+    assert rounds <= 3                                 # P50: every lane re-walks once from its true entry
+
+
+def test_fixture_block_and_special_shapes(libs):
+    blk = open(os.path.join(HERE, "golden", "p50_seed0_64k.lz4block"), "rb").read()
+    for cap in (65536, 65536 + 64, 65535, 65536 - 64, 70000, 100, 64, 0, -1):
+        for shift in range(4):
+            a, b, st = both(libs, blk, cap, shift)
+            assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]), (cap, shift, a[:2], b[:2], st)
+    # long literal runs (chains jump over whole segments), long matches, RLE, text
+    rng = np.random.default_rng(5)
+    orc = Oracle()
+    shapes = [bytes(rng.integers(0, 256, 30000, dtype=np.uint8)) + b"\x00" * 30000,
+              b"\x00" * 65536, b"ab" * 32768, bytes(rng.integers(0, 256, 65536 - 300, dtype=np.uint8)),
+              (bytes(rng.integers(0, 256, 3000, dtype=np.uint8)) + b"x" * 500) * 18,
+              b" ".join(bytes(rng.integers(97, 123, int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(9000))[:65536]]
+    for raw in shapes:
+        _, comp = orc.compress(raw, 1)
+        for cap in (len(raw), len(raw) + 64, len(raw) + 5000, len(raw) - 1):
+            a, b, st = both(libs, bytes(comp), cap, 1, with_marks=(len(comp) <= 65535 and cap <= 65536))
+            assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]), (len(raw), cap, a[:2], b[:2], st)
