@@ -36,6 +36,8 @@ def libs(tmp_path_factory):
     one.scan_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
     v2.scan_v2_host.restype = C.c_int
     v2.scan_v2_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_int)]
+    v2.scan_v2_fuzz.restype = C.c_longlong
+    v2.scan_v2_fuzz.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_longlong)]
     return one, v2
 
 
@@ -123,3 +125,21 @@ def test_fixture_block_and_special_shapes(libs):
         for cap in (len(raw), len(raw) + 64, len(raw) + 5000, len(raw) - 1):
             a, b, st = both(libs, bytes(comp), cap, 1, with_marks=(len(comp) <= 65535 and cap <= 65536))
             assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]), (len(raw), cap, a[:2], b[:2], st)
+
+
+def test_differential_fuzz_in_process(libs):
+    """Tens of thousands of mutated blocks, compared inside the emulator library (fast): the warp scan
+    must agree with the one-thread scan on the return value (incl. every error code), count and marks."""
+    _, v2 = libs
+    gen = Reference() if have_reference() else Oracle()
+    total = errors = 0
+    for seed, (proba, size, iters) in enumerate(((0.5, 65536, 12000), (0.9, 65536, 8000), (0.2, 65536, 4000), (0.0, 60000, 1500),
+                                                 (1.0, 65536, 1500), (0.5, 3000, 6000), (0.5, 4 << 20, 150), (0.9, 1 << 20, 300))):
+        raw = bytes(gen.datagen(size, proba, seed))
+        _, comp = gen.compress(raw, 1)
+        ne = C.c_longlong(0)
+        n = v2.scan_v2_fuzz(bytes(comp), len(comp), size, iters, seed, C.byref(ne))
+        assert n == iters, (proba, size, "first mismatch at case %d" % (-n - 1))
+        total += n
+        errors += ne.value
+    assert total > 30000 and errors > 10000
