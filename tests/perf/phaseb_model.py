@@ -18,6 +18,8 @@ Variants (--variant):
   inorder     CTA-wide in-order hand-out (chunks handed out in output order across all warps)
   park        base + a lane whose match piece is blocked parks the chunk and takes another one
               (one parked chunk per lane), resuming the parked chunk when it has no fresh one
+  v2          the uniform-body loop of lz4_phaseb_v2.h (same schedule as base, its own instruction counts)
+  v2x2        v2 with the body unrolled twice: a lane handles up to two pieces of its chunk per iteration
   twopass     chunks that lie inside ONE literal or match run ("simple": one unaligned 8-byte copy)
               are done first by a short uniform loop (est. 40 instr / iteration), the rest by the
               shipped piece loop
@@ -36,6 +38,8 @@ from oracle.pyoracle import Oracle, Reference, have_reference  # noqa: E402
 
 COST = dict(header=10, handout=45, literal=18, match=28, tail=28, store=12, nextseq=18, loop=2,
             simple_iter=40)
+# the uniform-body variant (lz4_phaseb_v2.h), per-path counts from its SASS
+COST_V2 = dict(header=18, handout=40, record=17, body=33, tail=15, store=13, step=6, loop=2)
 
 
 def parse_sequences(b, total):
@@ -124,9 +128,11 @@ def chunk_order(variant, total, nwarps=32):
 
 
 def simulate(blk, variant="base", nwarps=32, only_chunks=None):
+    per_tick = 2 if variant == "v2x2" else 1
+    v2 = variant in ("v2", "v2x2")
     """returns dict(iters, lane_iters, blocked, instr, pieces)"""
     total = blk.total
-    lists, global_list = chunk_order("base" if variant in ("park", "twopass") else variant, total, nwarps)
+    lists, global_list = chunk_order("base" if variant in ("park", "twopass", "v2", "v2x2") else variant, total, nwarps)
     if only_chunks is not None:
         if lists is not None:
             lists = [[c for c in l if c in only_chunks] for l in lists]
@@ -175,39 +181,49 @@ def simulate(blk, variant="base", nwarps=32, only_chunks=None):
             iters += 1
             lane_iters += len(act)
             any_lit = any_match = any_ok = any_store = any_next = False
+            sub_live = [False] * per_tick
             for l in act:
-                c, pcs, i = lanes[l]
-                pos, end, kind, src, off = pcs[i]
-                ok = True
-                if kind == 0:
-                    any_lit = True
-                else:
-                    any_match = True
-                    if off >= 8:
-                        ok = done[src >> 3] and done[(end - 1 - off) >> 3]
-                    elif off > 0:
-                        lo = max(src, 0)
-                        # bytes before this chunk must be final (same-chunk bytes come from the accumulator)
-                        if lo < c * 8:
-                            ok = bool(done[lo >> 3])
-                if not ok:
-                    blocked += 1
-                    if variant == "park":                  # park it; with a parked chunk already, swap the two
-                        parked[w][l], lanes[l] = lanes[l], parked[w][l]
-                    continue
-                any_ok = True
-                pieces_done += 1
-                i += 1
-                if i == len(pcs):
-                    newly_done.append(c)
-                    lanes[l] = None
-                    any_store = True
-                else:
-                    lanes[l][2] = i
-                    any_next = any_next or (pcs[i][2] == 0)      # a new sequence starts with its literal run
-            instr += (COST["header"] + COST["loop"] + (COST["handout"] if took else 0) + (COST["literal"] if any_lit else 0)
-                      + (COST["match"] if any_match else 0) + (COST["tail"] if any_ok else 0)
-                      + (COST["store"] if any_store else 0) + (COST["nextseq"] if any_next else 0))
+                for sub in range(per_tick):
+                    if lanes[l] is None:
+                        break
+                    c, pcs, i = lanes[l]
+                    pos, end, kind, src, off = pcs[i]
+                    ok = True
+                    sub_live[sub] = True
+                    if kind == 0:
+                        any_lit = True
+                    else:
+                        any_match = True
+                        if off >= 8:
+                            ok = done[src >> 3] and done[(end - 1 - off) >> 3]
+                        elif off > 0:
+                            lo = max(src, 0)
+                            # bytes before this chunk must be final (same-chunk bytes come from the accumulator)
+                            if lo < c * 8:
+                                ok = bool(done[lo >> 3])
+                    if not ok:
+                        blocked += 1
+                        if variant == "park":                  # park it; with a parked chunk already, swap the two
+                            parked[w][l], lanes[l] = lanes[l], parked[w][l]
+                        break
+                    any_ok = True
+                    pieces_done += 1
+                    i += 1
+                    if i == len(pcs):
+                        newly_done.append(c)
+                        lanes[l] = None
+                        any_store = True
+                    else:
+                        lanes[l][2] = i
+                        any_next = any_next or (pcs[i][2] == 0)      # a new sequence starts with its literal run
+            if v2:
+                body = COST_V2["record"] + COST_V2["body"] + COST_V2["tail"] + COST_V2["step"]
+                instr += (COST_V2["header"] + COST_V2["loop"] + (COST_V2["handout"] if took else 0)
+                          + body * sum(1 for x in sub_live if x) + (COST_V2["store"] if any_store else 0))
+            else:
+                instr += (COST["header"] + COST["loop"] + (COST["handout"] if took else 0) + (COST["literal"] if any_lit else 0)
+                          + (COST["match"] if any_match else 0) + (COST["tail"] if any_ok else 0)
+                          + (COST["store"] if any_store else 0) + (COST["nextseq"] if any_next else 0))
         for c in newly_done:
             done[c] = True
         if variant == "park":
@@ -236,7 +252,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=4)
     ap.add_argument("--proba", type=float, default=0.5)
-    ap.add_argument("--variant", nargs="*", default=["base", "strip128", "inorder", "park", "twopass"])
+    ap.add_argument("--variant", nargs="*", default=["base", "v2", "v2x2", "strip128", "inorder", "park", "twopass"])
     a = ap.parse_args()
     codec = Reference() if have_reference() else Oracle()
     # block 0 of a generated buffer is an outlier (dependency chains ~190 deep against ~25 for every
