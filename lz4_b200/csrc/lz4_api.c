@@ -42,7 +42,7 @@ static int cuda_fail(cudaError_t e, const char* where)
 
 const char* LZ4B200_last_cuda_error(void) { return g_cuda_error; }
 uint64_t LZ4B200_launch_count(void) { return lz4k_launch_count(); }
-/* not part of the public header: developer hook used by profiles/phase_timing.py */
+/* not part of the public header: developer hook used by tests/perf/phase_timing.py */
 __attribute__((visibility("default"))) int LZ4B200_debug_phase_cycles(unsigned long long* out8) { return lz4k_debug_phase_cycles(out8); }
 int LZ4B200_device_count(void)
 {
