@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblz4_b200.so")
+# LZ4_B200_LIBRARY=<path> loads a developer variant built with `python -m lz4_b200.build --out <path> -D...`
+LIB_PATH = os.environ.get("LZ4_B200_LIBRARY") or os.path.join(_HERE, "liblz4_b200.so")
 
 # every symbol include/lz4_b200.h declares: (name, restype, argtypes)
 _vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t

@@ -49,26 +49,35 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, out=None, extra_defines=()):
+    """Build the library.  `out` / `extra_defines` are for developer variants (experimental kernels built
+    next to the default library, e.g. out=build/liblz4_b200_pbv2.so, extra_defines=["LZ4K_PHASEB_V2"]);
+    load one with LZ4_B200_LIBRARY=<path> (lz4_b200/_lib.py)."""
+    lib = out or LIB
+    if out is None and not extra_defines and not force and not _stale():
         return LIB
     if not os.path.exists(NVCC):
         raise RuntimeError("nvcc not found at %s" % NVCC)
     gcc = shutil.which("gcc") or "gcc"
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
-    ko = os.path.join(objdir, "lz4_kernels.o")
-    ao = os.path.join(objdir, "lz4_api.o")
-    log = _run([NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+    tag = "" if out is None else "_" + os.path.splitext(os.path.basename(out))[0]
+    ko = os.path.join(objdir, "lz4_kernels%s.o" % tag)
+    ao = os.path.join(objdir, "lz4_api%s.o" % tag)
+    defs = ["-D" + d for d in extra_defines]
+    log = _run([NVCC] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) +
                ["-c", os.path.join(CSRC, "lz4_kernels.cu"), "-o", ko])
     log += _run([gcc] + CC_FLAGS + ["-c", os.path.join(CSRC, "lz4_api.c"), "-o", ao])
-    log += _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, ko, ao,
+    log += _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, ko, ao,
                  "-Xlinker", "-Bsymbolic", "-lpthread"])
     if verbose:
         print(log)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
-    print("built", LIB)
+    # python -m lz4_b200.build [--force] [--out PATH] [-DNAME ...]
+    argv = sys.argv[1:]
+    out_path = argv[argv.index("--out") + 1] if "--out" in argv else None
+    defines = [a[2:] for a in argv if a.startswith("-D")]
+    print("built", build(force="--force" in argv, verbose=True, out=out_path, extra_defines=defines))
