@@ -16,7 +16,7 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
 SOURCES = ["lz4_kernels.cu", "lz4_api.c"]
-HEADERS = [os.path.join(CSRC, "lz4_kernels.h"), os.path.join(CSRC, "lz4_phaseb_v2.h"),
+HEADERS = [os.path.join(CSRC, "lz4_kernels.h"), os.path.join(CSRC, "lz4_phaseb_v2.h"), os.path.join(CSRC, "lz4_rows_core.h"),
            os.path.join(CSRC, "lz4_scan_core.h"), os.path.join(CSRC, "lz4_scan_v2.h"),
            os.path.join(ROOT, "include", "lz4_b200.h")]
 

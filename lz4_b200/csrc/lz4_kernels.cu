@@ -14,6 +14,8 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <stddef.h>
 #include "lz4_kernels.h"
 
 namespace {
@@ -48,6 +50,7 @@ __device__ unsigned long long g_loopStats[4];    // phase B: warp iterations, la
  * emulators under tests/emul/, see the header */
 #define LZ4_SCAN_CORE_CONSTANTS
 #include "lz4_scan_core.h"
+#include "lz4_rows_core.h"
 
 /* low 5 bytes at p (for the 5-byte hash, lz4.c:785-791) */
 __device__ __forceinline__ uint64_t ld40u(const uint8_t* p)
@@ -554,6 +557,276 @@ __global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_d
 }
 
 /* =============================================================================================
+ * expand (rows): one CTA per 64 KB block, one output BYTE per thread, waves + run table
+ *
+ * See lz4_rows_core.h for the formulation.  Per block:
+ *   TMA bulk load  : compressed block HBM -> smem (`in`, placed below `out` in the window)
+ *   runs, pass 1   : one lane per sequence re-reads its token (marks from the scan) and sets one bit
+ *                    per run start (literal run, match run, pieces of self-overlapping matches)
+ *   rank           : rows[r].y = (run starts before row r) - 1
+ *   runs, pass 2   : the same lanes write delta(run) at the run's rank
+ *   waves          : kWave bytes per CTA barrier; thread t handles bytes t, t+1024, ... of the wave:
+ *                    rank -> delta -> (follow sources inside the wave) -> LDS.U8 -> STS.U8
+ *   TMA bulk store : decoded block smem -> HBM
+ * ============================================================================================= */
+#ifndef LZ4K_ROWS_RPT
+#define LZ4K_ROWS_RPT 4                      /* rows per thread per wave: wave = 1024 * RPT bytes */
+#endif
+constexpr int kRowsThreads = 1024;
+constexpr int kRowsRpt = LZ4K_ROWS_RPT;
+constexpr int kWave = kRowsThreads * kRowsRpt;
+constexpr int kRowsCache = 3;                /* sequences per thread whose parse is kept in registers between the passes */
+
+struct RowsSmem {
+    alignas(16) uint8_t zero[16];            /* always-zero cell: source of offset-0 matches (lz4.c:2407) */
+    alignas(16) uint8_t in[kInBytes];        /* staged compressed block; keeps the source's 16-byte phase */
+    alignas(16) uint8_t out[65536];          /* output window; MUST lie above `zero` and `in` */
+    alignas(16) uint32_t tab[kRowsMaxRuns];  /* delta per run */
+    alignas(8) uint2 rows[2048];             /* {run-start bits of the row, run starts before the row - 1} */
+    uint32_t warpSum[32];
+    alignas(8) uint64_t mbar;
+    uint32_t nextIdx[2];
+    uint32_t nRuns;
+};
+static_assert(sizeof(RowsSmem) <= 232448, "RowsSmem exceeds the 227 KB of shared memory a CTA can opt in to");
+
+__device__ __forceinline__ uint2 lds_u64(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lanemask_le()
+{
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+
+/* One wave of the rows kernel for one thread: bytes p0 + r*1024 (r < kRowsRpt) of the wave that starts at shared
+ * address waveS.  FULL: the whole wave lies inside the block (no bounds checks).  All addresses are 32-bit
+ * shared-window addresses; every load of the wave is issued before its first store. */
+template <bool FULL>
+__device__ __forceinline__ void rows_wave(const uint32_t p0, const uint32_t waveS, const uint32_t lim, const uint32_t outS,
+                                          const uint32_t rowsS, const uint32_t tabS, const uint32_t zeroS, const uint32_t le)
+{
+    const uint32_t rowAddr = rowsS + ((p0 >> 5) << 3);
+    uint32_t sa[kRowsRpt];                                     /* shared address of each byte's source */
+    #pragma unroll
+    for (int r = 0; r < kRowsRpt; r++) {
+        sa[r] = zeroS;
+        if (FULL || p0 + (uint32_t)(r * kRowsThreads) < lim) {
+            const uint2 row = lds_u64(rowAddr + (uint32_t)(r * (kRowsThreads / 32) * 8));
+            const uint32_t j = row.y + (uint32_t)__popc(row.x & le);
+            sa[r] = outS + p0 + (uint32_t)(r * kRowsThreads) + lds_u32(tabS + (j << 2));
+        }
+    }
+    uint32_t hi = sa[0];
+    #pragma unroll
+    for (int r = 1; r < kRowsRpt; r++) hi = max(hi, sa[r]);
+    if (hi >= waveS) {                                         /* sources inside this wave: follow them */
+        #pragma unroll
+        for (int r = 0; r < kRowsRpt; r++) {
+            uint32_t x = sa[r];
+            while (x >= waveS) {
+                const uint32_t q = x - outS;
+                const uint2 row = lds_u64(rowsS + ((q >> 5) << 3));
+                const uint32_t j = row.y + (uint32_t)__popc(row.x & (0xFFFFFFFFu >> (31u - (q & 31u))));
+                x += lds_u32(tabS + (j << 2));
+            }
+            sa[r] = x;
+        }
+    }
+    uint32_t v[kRowsRpt];
+    #pragma unroll
+    for (int r = 0; r < kRowsRpt; r++) v[r] = lds_u8(sa[r]);
+    #pragma unroll
+    for (int r = 0; r < kRowsRpt; r++)
+        if (FULL || p0 + (uint32_t)(r * kRowsThreads) < lim) sts_u8(outS + p0 + (uint32_t)(r * kRowsThreads), v[r]);
+}
+
+__global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_decode_args a)
+{
+    extern __shared__ __align__(16) uint8_t smemRaw[];
+    RowsSmem& S = *reinterpret_cast<RowsSmem*>(smemRaw);
+    uint8_t* const win = smemRaw;                               /* the window: one byte array over the whole struct */
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const WsView w = ws_view(a.workspace, a.nBlocks);
+    const uint32_t fastCount = w.hdr->fastCount;
+    const uint32_t le = lanemask_le();
+    const uint32_t outA = (uint32_t)offsetof(RowsSmem, out);
+    const int zeroDelta0 = (int)offsetof(RowsSmem, zero) - (int)outA;
+    const uint32_t sBase = smem_u32(smemRaw);
+    const uint32_t outS = sBase + outA, zeroS = sBase + (uint32_t)offsetof(RowsSmem, zero);
+    const uint32_t rowsS = sBase + (uint32_t)offsetof(RowsSmem, rows), tabS = sBase + (uint32_t)offsetof(RowsSmem, tab);
+    uint32_t parity = 0;
+
+    if (tid == 0) mbar_init(&S.mbar, 1);
+    if (tid < 4) reinterpret_cast<uint32_t*>(S.zero)[tid] = 0;
+    if (tid == 0) S.nextIdx[0] = atomicAdd(&w.hdr->fastCursor, 1u);
+    __syncthreads();
+#ifdef LZ4K_PHASE_TIMING
+    long long tPhase = clock64();
+#endif
+
+    for (uint32_t it = 0;; it++) {
+        const uint32_t idx = S.nextIdx[it & 1];
+        if (idx >= fastCount) break;
+        if (tid == 0) S.nextIdx[(it + 1) & 1] = atomicAdd(&w.hdr->fastCursor, 1u);   // read after this block's barriers
+        const int64_t b = w.fastList[idx];
+        const uint8_t* src = a.src + a.srcOff[b];
+        const int n = a.srcSize[b];
+        const int total = a.outSize[b];
+        const int nseq = (int)w.nSeq[b];
+        uint8_t* dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
+        const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+        const uint32_t loadBytes = (uint32_t)((head + n + 15) & ~15);
+
+        if (tid == 0) {
+            mbar_expect_tx(&S.mbar, loadBytes);
+            for (uint32_t o = 0; o < loadBytes; o += 16384u)
+                tma_load_1d(S.in + o, src - head + o, min(16384u, loadBytes - o), &S.mbar);
+        }
+        for (int k = tid; k < 2048; k += kRowsThreads) S.rows[k] = make_uint2(0u, 0u);
+        /* this thread's first marks, fetched while the TMA load is in flight */
+        const uint32_t* marks = w.marks + b * kMaxSeqFast;
+        uint32_t mk[kRowsCache], mkn[kRowsCache];
+        #pragma unroll
+        for (int i = 0; i < kRowsCache; i++) {
+            const int k = tid + i * kRowsThreads;
+            mk[i] = (k < nseq) ? marks[k] : 0u;
+            mkn[i] = (k + 1 < nseq) ? marks[k + 1] : 0u;
+        }
+        __syncthreads();                                   /* rows are zero */
+        PHASE_MARK(0);                                     // fetch + zeroing
+        while (!mbar_try_wait(&S.mbar, parity)) { }
+        parity ^= 1;
+        PHASE_MARK(1);                                     // TMA load wait
+
+        /* ---- runs, pass 1: one bit per run start ---- */
+        const uint8_t* in = S.in + head;
+        const uint32_t inA = (uint32_t)offsetof(RowsSmem, in) + (uint32_t)head;
+        auto setBit = [&](int s, int) { atomicOr(&S.rows[s >> 5].x, 1u << (s & 31)); };
+        RwSeq sq[kRowsCache];
+        #pragma unroll
+        for (int i = 0; i < kRowsCache; i++) {
+            const int k = tid + i * kRowsThreads;
+            if (k < nseq) {
+                sq[i] = rw_parse(in, mk[i], mkn[i], k, k + 1 == nseq, total);
+                if (sq[i].ll > 0) setBit(sq[i].op, 0);
+                if (sq[i].mlen > 0) rw_match_runs(sq[i].m, sq[i].off, sq[i].mlen, zeroDelta0, setBit);
+            }
+        }
+        for (int k = tid + kRowsCache * kRowsThreads; k < nseq; k += kRowsThreads) {
+            const bool last = (k + 1 == nseq);
+            const RwSeq s = rw_parse(in, marks[k], last ? 0u : marks[k + 1], k, last, total);
+            if (s.ll > 0) setBit(s.op, 0);
+            if (s.mlen > 0) rw_match_runs(s.m, s.off, s.mlen, zeroDelta0, setBit);
+        }
+        __syncthreads();
+        PHASE_MARK(2);                                     // pass 1
+
+        /* ---- rank: rows[r].y = (number of run starts in rows [0, r)) - 1 ---- */
+        {
+            constexpr int WPT = 2048 / kRowsThreads;
+            uint32_t cnt[WPT], x = 0;
+            #pragma unroll
+            for (int j = 0; j < WPT; j++) { cnt[j] = __popc(S.rows[tid * WPT + j].x); x += cnt[j]; }
+            uint32_t incl = x;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += y; }
+            if (lane == 31) S.warpSum[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t v = S.warpSum[lane];
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, v, d); if (lane >= d) v += y; }
+                S.warpSum[lane] = v;
+                if (lane == 31) S.nRuns = v;
+            }
+            __syncthreads();
+            uint32_t ex = incl - x + (warp ? S.warpSum[warp - 1] : 0);
+            #pragma unroll
+            for (int j = 0; j < WPT; j++) { S.rows[tid * WPT + j].y = ex - 1u; ex += cnt[j]; }
+        }
+        const uint32_t nRuns = S.nRuns;
+        if (tid == 0) tma_wait_read0();                    /* the previous block's bulk store has finished reading S.out */
+        __syncthreads();
+        PHASE_MARK(3);                                     // rank
+        if (nRuns > (uint32_t)kRowsMaxRuns) {              /* (pathological) too many runs for the table: generic kernel */
+            if (tid == 0) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
+            continue;
+        }
+
+        /* ---- runs, pass 2: delta of every run at its rank ---- */
+        {
+            auto emit = [&](const RwSeq& s) {
+                if (s.ll > 0) S.tab[rw_rank(S.rows, (uint32_t)s.op)] = (inA + (uint32_t)s.ls) - (outA + (uint32_t)s.op);
+                if (s.mlen > 0) {
+                    uint32_t j = rw_rank(S.rows, (uint32_t)s.m);
+                    rw_match_runs(s.m, s.off, s.mlen, zeroDelta0, [&](int, int d) { S.tab[j++] = (uint32_t)d; });
+                }
+            };
+            #pragma unroll
+            for (int i = 0; i < kRowsCache; i++) {
+                const int k = tid + i * kRowsThreads;
+                if (k < nseq) emit(sq[i]);
+            }
+            for (int k = tid + kRowsCache * kRowsThreads; k < nseq; k += kRowsThreads) {
+                const bool last = (k + 1 == nseq);
+                emit(rw_parse(in, marks[k], last ? 0u : marks[k + 1], k, last, total));
+            }
+        }
+        __syncthreads();
+        PHASE_MARK(4);                                     // pass 2
+
+        /* ---- waves ---- */
+        {
+            const int nWaves = (total + kWave - 1) / kWave;
+            for (int wv = 0; wv < nWaves; wv++) {
+                const uint32_t p0 = (uint32_t)(wv * kWave + tid);
+                if ((wv + 1) * kWave <= total) rows_wave<true>(p0, outS + (uint32_t)(wv * kWave), 0xFFFFFFFFu, outS, rowsS, tabS, zeroS, le);
+                else rows_wave<false>(p0, outS + (uint32_t)(wv * kWave), (uint32_t)total, outS, rowsS, tabS, zeroS, le);
+                if (wv == nWaves - 1) fence_proxy_async();  /* generic-proxy writes of `out` before the bulk store reads them */
+                __syncthreads();
+            }
+        }
+        PHASE_MARK(5);                                     // waves
+
+        /* ---- store: smem -> HBM ---- */
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const uint32_t bulk = (uint32_t)total & ~15u;
+            if (tid == 0 && bulk) {
+                for (uint32_t o = 0; o < bulk; o += 16384u) tma_store_1d(dst + o, S.out + o, min(16384u, bulk - o));
+                tma_commit();
+            }
+            if (tid < (total & 15)) dst[bulk + tid] = S.out[bulk + tid];
+        } else {
+            for (int k = tid; k < total; k += kRowsThreads) dst[k] = S.out[k];
+        }
+        PHASE_MARK(6);                                     // store issue
+    }
+    if (tid == 0) tma_wait_all0();
+}
+
+/* =============================================================================================
  * encode: one warp per block, byte-identical replay of LZ4_compress_generic_validated
  * ============================================================================================= */
 
@@ -875,8 +1148,12 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (a->nBlocks == 0) return 0;
-    {   /* opt in to the 205 KB of dynamic shared memory (per device, cheap to repeat) */
+    static int impl = -1;                 /* developer A/B switch: LZ4K_EXPAND_IMPL=pieces selects the round-1 kernel */
+    if (impl < 0) { const char* v = getenv("LZ4K_EXPAND_IMPL"); impl = (v && v[0] == 'p') ? 1 : 0; }
+    {   /* opt in to the > 200 KB of dynamic shared memory (per device, cheap to repeat) */
         cudaError_t e = cudaFuncSetAttribute(lz4_expand_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(lz4_expand_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
         if (e != cudaSuccess) return (int)e;
     }
     if (phases & 1) {
@@ -900,7 +1177,8 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         cudaError_t e = cudaMemsetAsync(&w.hdr->fastCursor, 0, sizeof(uint32_t), s);
         if (e != cudaSuccess) return (int)e;
         int64_t grid = a->nBlocks < sms ? a->nBlocks : sms;          // persistent: one CTA per SM
-        lz4_expand_fast_kernel<<<(unsigned)grid, kFastThreads, sizeof(FastSmem), s>>>(*a);
+        if (impl == 1) lz4_expand_fast_kernel<<<(unsigned)grid, kFastThreads, sizeof(FastSmem), s>>>(*a);
+        else lz4_expand_rows_kernel<<<(unsigned)grid, kRowsThreads, sizeof(RowsSmem), s>>>(*a);
         g_launches++;
         const int threads = 128;   // 4 warps = 4 blocks per CTA
         const int64_t grid2 = (a->nBlocks * 32 + threads - 1) / threads;

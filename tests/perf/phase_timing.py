@@ -40,7 +40,9 @@ def main():
     t1.record()
     torch.cuda.synchronize()
     raw.LZ4B200_debug_phase_cycles(buf)
-    names = ["fetch+zero", "tma load wait", "phase A", "rank", "prev store wait", "phase B", "store issue", "-"]
+    names = (["fetch+zero", "tma load wait", "runs pass 1", "rank + prev store", "runs pass 2", "waves", "store issue", "-"]
+             if os.environ.get("LZ4K_EXPAND_IMPL", "")[:1] != "p" else
+             ["fetch+zero", "tma load wait", "phase A", "rank", "prev store wait", "phase B", "store issue", "-"])
     tot = sum(buf[:8])
     print("expand ms per launch %.3f, blocks %d" % (t0.elapsed_time(t1) / reps, n_blocks))
     for n, v in zip(names, buf[:8]):

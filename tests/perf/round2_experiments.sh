@@ -15,7 +15,7 @@ PY
 declare -A DEFS=( [default]="" [pbv2]="-DLZ4K_PHASEB_V2" [scanv2]="-DLZ4K_SCAN_V2" [both]="-DLZ4K_PHASEB_V2 -DLZ4K_SCAN_V2" )
 for v in default pbv2 scanv2 both; do
   lib=lz4_b200/build/liblz4_b200_$v.so
-  python -m lz4_b200.build --out $lib ${DEFS[$v]} > gpurun_out/exp_$v.build.txt 2>&1 || { echo "$v: build failed"; continue; }
+  [ -f $lib ] || python -m lz4_b200.build --out $lib ${DEFS[$v]} > gpurun_out/exp_$v.build.txt 2>&1 || { echo "$v: build failed"; continue; }
   export LZ4_B200_LIBRARY=$PWD/$lib
   {
     echo "== $v: GPU parity tests"
