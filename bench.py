@@ -124,47 +124,81 @@ def cpu_decompress_rate(orc, codec, comp, offs, sizes, n_blocks, threads, passes
 
 
 def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref when it was compiled, else the oracle port) on this box's
+    host cores: all threads, one pinned worker per CPU, static block partition (programs/bench.c:464-555 loops one
+    thread the same way), every buffer first-touched by the worker that uses it, compressed input packed like
+    the GPU arm's.  `value` comes from the MEDIAN step (robust against a disturbed pass); best and mean are
+    reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     orc, codec, kind = cpu_codec()
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or os.cpu_count() or 1
     gib = args.gib if cores >= 32 else min(args.gib, 1.0)
     n_blocks = int(gib * (1 << 30)) // BLOCK
-    data = orc.datagen_mt(n_blocks * BLOCK, SEG, args.proba, 0, cores)
+    data = np.empty(n_blocks * BLOCK, dtype=np.uint8)
+    orc.first_touch(data, BLOCK, n_blocks, cores)
+    orc.datagen_mt(n_blocks * BLOCK, SEG, args.proba, 0, cores, out=data)
     cap = orc.compress_bound(BLOCK)
     stride = (cap + 15) // 16 * 16
     slots = np.empty(n_blocks * stride, dtype=np.uint8)
-    tc, csz = orc.time_compress(codec, data, BLOCK, slots, stride, args.accel, cores)
-    assert tc > 0
-    offs = np.arange(n_blocks, dtype=np.int64) * stride
+    orc.first_touch(slots, stride, n_blocks, cores)
+    tcs = []
+    for _ in range(3):
+        tc, csz = orc.time_compress(codec, data, BLOCK, slots, stride, args.accel, cores)
+        assert tc > 0
+        tcs.append(tc)
+    offs = np.zeros(n_blocks + 1, dtype=np.int64)
+    np.cumsum(csz, out=offs[1:])
+    packed = np.empty(int(offs[-1]) + 16, dtype=np.uint8)
+    orc.pack(slots, stride, csz, offs[:-1].copy(), packed, cores)       # the GPU arm decodes a packed stream too
+    del slots
+    offs = offs[:-1].copy()
     out = np.empty(n_blocks * BLOCK, dtype=np.uint8)
-    for _ in range(args.warmup):
-        orc.time_decompress(codec, slots, offs, csz, out, BLOCK, cores)
-    t_total = 0.0
+    orc.first_touch(out, BLOCK, n_blocks, cores)
+    t1, _ = orc.time_decompress(codec, packed, offs[:min(n_blocks, 2048)], csz[:min(n_blocks, 2048)], out, BLOCK, 1)
+    single = min(n_blocks, 2048) * BLOCK / t1 / GB
+    for _ in range(max(args.warmup, 1)):
+        orc.time_decompress(codec, packed, offs, csz, out, BLOCK, cores)
+    times = []
     for _ in range(args.steps):
-        t, rets = orc.time_decompress(codec, slots, offs, csz, out, BLOCK, cores)
+        t, rets = orc.time_decompress(codec, packed, offs, csz, out, BLOCK, cores)
         assert t > 0 and (rets == BLOCK).all()
-        t_total += t
+        times.append(t)
     assert (out == data).all(), "reference round trip mismatch"
-    value = n_blocks * BLOCK * args.steps / t_total / GB
-    sample = "%d blocks of %d KB (%.2f GiB) datagen P%d, all %d host threads, static partition" % (
-        n_blocks, BLOCK // 1024, n_blocks * BLOCK / (1 << 30), round(args.proba * 100), cores)
+    med, best, mean = float(np.median(times)), min(times), sum(times) / len(times)
+    nbytes = n_blocks * BLOCK
+    value = nbytes / med / GB
+    sample = "%d blocks of %d KB (%.2f GiB) datagen P%d, %d pinned host threads (one per CPU), static partition, packed input" % (
+        n_blocks, BLOCK // 1024, nbytes / (1 << 30), round(args.proba * 100), cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(1e3 * t_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": round(1e3 * med, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "decompress %d x %d KB blocks, datagen P%d, CPU %s lib/lz4.c" % (
-            n_blocks, BLOCK // 1024, round(args.proba * 100), kind), "block_bytes": BLOCK, "blocks": n_blocks,
-            "ratio": round(n_blocks * BLOCK / float(csz.sum()), 4)},
+        "config": workload_config(n_blocks, gib, args.proba, args.accel, nbytes / float(csz.sum())),
+        "timing": {"value_from": "median step", "best_GBps": round(nbytes / best / GB, 3),
+                   "median_GBps": round(value, 3), "mean_GBps": round(nbytes / mean / GB, 3),
+                   "spread": round(max(times) / best, 3)},
         "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample,
-                         "compress_GBps_all_threads": round(n_blocks * BLOCK / tc / GB, 3)},
+                         "single_thread_GBps": round(single, 3),
+                         "compress_GBps_all_threads": round(nbytes / min(tcs) / GB, 3)},
         "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if max(times) / best > 1.5:
+        line["warning"] = "reference passes disagree by more than 1.5x (%.1f .. %.1f GB/s): the host was disturbed" % (
+            nbytes / max(times) / GB, nbytes / best / GB)
     print(json.dumps(line))
     return 0
+
+
+def workload_config(n_blocks, gib, proba, accel, ratio):
+    """`config` of the JSON line: identical text for both arms (the driver compares it)."""
+    return {"workload": "decompress-only, %d independent %d KB blocks per GPU (%.2f GiB), tests/datagen P%d "
+                        "(RDG_genBuffer per 64 MiB segment, seed=rank*64+k), compressed by LZ4_compress_fast accel %d"
+                        % (n_blocks, BLOCK // 1024, gib, round(proba * 100), accel),
+            "block_bytes": BLOCK, "blocks_per_gpu": n_blocks, "ratio": round(ratio, 4)}
 
 
 # --------------------------------------------------------------------------------------------

@@ -92,8 +92,13 @@ LZ4B200_API const char* LZ4B200_last_cuda_error(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 LZ4B200_API uint64_t LZ4B200_launch_count(void);
 
-/* Bytes of device workspace LZ4B200_decompress_blocks needs for nBlocks blocks. */
+/* Bytes of device workspace LZ4B200_decompress_blocks needs for nBlocks blocks of ANY capacity
+ * (worst case: 32 KB of sequence marks per block). */
 LZ4B200_API size_t LZ4B200_decompress_workspace_bytes(int64_t nBlocks);
+/* The exact requirement of one call: perBlockCaps != 0 when d_dstCap is passed, else the uniform dstCap.
+ * Marks are sized by the capacity (dstCap/4 + 2 slots, at most 8192; none for blocks above 64 KB), so
+ * batches of small blocks need little workspace.  Always <= LZ4B200_decompress_workspace_bytes(nBlocks). */
+LZ4B200_API size_t LZ4B200_decompress_workspace_bytes_for(int64_t nBlocks, int perBlockCaps, int32_t dstCap);
 
 /*
  * Decompress nBlocks independent LZ4 blocks (the batched LZ4_decompress_safe; replaces the serial
@@ -104,6 +109,10 @@ LZ4B200_API size_t LZ4B200_decompress_workspace_bytes(int64_t nBlocks);
  *                   malformed; other blocks are unaffected)
  * Output regions of different blocks must not overlap.  Enqueued on `stream`; returns LZ4B200_OK
  * once enqueued.
+ * Readable padding: blocks of up to 65 535 bytes are staged by 16-byte-granular bulk loads, so the 16-byte
+ * granules that hold the first and the last byte of every block are read in full -- up to 15 bytes before
+ * d_src + d_srcOff[i] and after the block's end must be readable device memory (e.g. 16 bytes of slack at both
+ * ends of d_src; bytes of neighbouring blocks are fine).  Nothing outside a block influences its result.
  */
 LZ4B200_API int LZ4B200_decompress_blocks(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
                                           void* d_dst, const int64_t* d_dstOff, int64_t dstStride,

@@ -28,6 +28,7 @@ PROTOTYPES = [
     ("LZ4B200_last_cuda_error", C.c_char_p, []),
     ("LZ4B200_launch_count", C.c_uint64, []),
     ("LZ4B200_decompress_workspace_bytes", _sz, [_i64]),
+    ("LZ4B200_decompress_workspace_bytes_for", _sz, [_i64, C.c_int, _i32]),
     ("LZ4B200_decompress_blocks", C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _i64, _vp, _sz, _vp]),
     ("LZ4B200_decompress_blocks_phased", C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _i64, _vp, _sz, C.c_int, _vp]),
     ("LZ4B200_compress_blocks", C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _i32, C.c_int, _vp, _i64, _vp]),

@@ -16,20 +16,14 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
 SOURCES = ["lz4_kernels.cu", "lz4_api.c"]
-HEADERS = [os.path.join(CSRC, "lz4_kernels.h"), os.path.join(CSRC, "lz4_phaseb_v2.h"), os.path.join(CSRC, "lz4_rows_core.h"),
-           os.path.join(CSRC, "lz4_scan_core.h"), os.path.join(CSRC, "lz4_scan_v2.h"),
+HEADERS = [os.path.join(CSRC, "lz4_kernels.h"), os.path.join(CSRC, "lz4_rows_core.h"),
+           os.path.join(CSRC, "lz4_scan_core.h"), os.path.join(CSRC, "lz4_scan_par.h"),
            os.path.join(ROOT, "include", "lz4_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math", "-diag-suppress", "177"]
-if os.environ.get("LZ4K_FAST_THREADS"):        # developer knob: CTA size of the fast expand kernel
-    NVCC_FLAGS.append("-DLZ4K_FAST_THREADS=" + os.environ["LZ4K_FAST_THREADS"])
 if os.environ.get("LZ4K_PHASE_TIMING"):          # developer build: per-phase clock64 counters
     NVCC_FLAGS.append("-DLZ4K_PHASE_TIMING")
-if os.environ.get("LZ4K_PHASEB_V2"):             # developer build: experimental phase B (csrc/lz4_phaseb_v2.h)
-    NVCC_FLAGS.append("-DLZ4K_PHASEB_V2")
-if os.environ.get("LZ4K_SCAN_V2"):               # developer build: experimental warp-per-block scan (csrc/lz4_scan_v2.h)
-    NVCC_FLAGS.append("-DLZ4K_SCAN_V2")
 CC_FLAGS = ["-O2", "-fPIC", "-std=c99", "-Wall", "-Wextra", "-fvisibility=hidden",
             "-I" + os.path.join(CUDA_HOME, "include")]
 

@@ -122,6 +122,10 @@ done:
 /* batch layer: device pointers                                                                */
 /* ------------------------------------------------------------------------------------------ */
 size_t LZ4B200_decompress_workspace_bytes(int64_t nBlocks) { return lz4k_decode_workspace_bytes(nBlocks); }
+size_t LZ4B200_decompress_workspace_bytes_for(int64_t nBlocks, int perBlockCaps, int32_t dstCap)
+{
+    return lz4k_decode_workspace_bytes_for(nBlocks, perBlockCaps, dstCap);
+}
 
 int LZ4B200_decompress_blocks_phased(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
                               void* d_dst, const int64_t* d_dstOff, int64_t dstStride,
@@ -134,7 +138,7 @@ int LZ4B200_decompress_blocks_phased(const void* d_src, const int64_t* d_srcOff,
     if (nBlocks < 0) return LZ4B200_ERR_ARG;
     if (nBlocks == 0) return LZ4B200_OK;
     if (!d_src || !d_srcOff || !d_srcSize || !d_dst || !d_outSize || !d_workspace) return LZ4B200_ERR_ARG;
-    if (workspaceBytes < lz4k_decode_workspace_bytes(nBlocks)) return LZ4B200_ERR_ARG;
+    if (workspaceBytes < lz4k_decode_workspace_bytes_for(nBlocks, d_dstCap != NULL, dstCap)) return LZ4B200_ERR_ARG;
     a.src = (const uint8_t*)d_src; a.srcOff = d_srcOff; a.srcSize = d_srcSize;
     a.dst = (uint8_t*)d_dst; a.dstOff = d_dstOff; a.dstStride = dstStride;
     a.dstCapArr = d_dstCap; a.dstCap = dstCap; a.outSize = d_outSize; a.nBlocks = nBlocks;
@@ -214,7 +218,7 @@ int LZ4B200_decompress_blocks_host(const void* h_src, const int64_t* h_srcOff, c
         }
         inBytes = (size_t)(hi - lo);
         metaBytes = (size_t)cnt * (sizeof(int64_t) + 2 * sizeof(int32_t));
-        wsBytes = lz4k_decode_workspace_bytes(cnt);
+        wsBytes = lz4k_decode_workspace_bytes_for(cnt, 0, dstCap);
         CU(cudaStreamSynchronize(st));                      /* slot reuse: previous chunk on it is finished */
         flush_slot(slot);
         if ((rc = grow(&g_ctx.d_in[slot], &g_ctx.in_cap[slot], inBytes + 16)) != LZ4B200_OK) goto done;
@@ -399,7 +403,7 @@ int LZ4_decompress_safe(const char* src, char* dst, int compressedSize, int dstC
     if ((rc = grow(&g_ctx.d_in[0], &g_ctx.in_cap[0], (size_t)compressedSize + 16)) != LZ4B200_OK) goto done;
     if ((rc = grow(&g_ctx.d_out[0], &g_ctx.out_cap[0], (size_t)dstCapacity + 16)) != LZ4B200_OK) goto done;
     if ((rc = grow(&g_ctx.d_meta[0], &g_ctx.meta_cap[0], 64)) != LZ4B200_OK) goto done;
-    if ((rc = grow(&g_ctx.d_ws[0], &g_ctx.ws_cap[0], lz4k_decode_workspace_bytes(1))) != LZ4B200_OK) goto done;
+    if ((rc = grow(&g_ctx.d_ws[0], &g_ctx.ws_cap[0], lz4k_decode_workspace_bytes_for(1, 0, dstCapacity))) != LZ4B200_OK) goto done;
     d_off = (int64_t*)g_ctx.d_meta[0];
     d_size = (int32_t*)(d_off + 1);
     d_ret = d_size + 1;

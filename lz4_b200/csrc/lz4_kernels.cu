@@ -33,10 +33,6 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 unsigned long long g_launches = 0;
 
-#ifdef LZ4K_PHASEB_V2
-#include "lz4_phaseb_v2.h"     /* experimental phase B ("uniform body"); not in the default build */
-#endif
-
 /* optional phase timing of the fast expand kernel (thread 0 of each CTA; enabled with -DLZ4K_PHASE_TIMING) */
 __device__ unsigned long long g_phaseCycles[8];
 __device__ unsigned long long g_loopStats[4];    // phase B: warp iterations, lane-iterations with a piece, blocked lane-iterations, pieces done
@@ -50,6 +46,7 @@ __device__ unsigned long long g_loopStats[4];    // phase B: warp iterations, la
  * emulators under tests/emul/, see the header */
 #define LZ4_SCAN_CORE_CONSTANTS
 #include "lz4_scan_core.h"
+#include "lz4_scan_par.h"
 #include "lz4_rows_core.h"
 
 /* low 5 bytes at p (for the 5-byte hash, lz4.c:785-791) */
@@ -65,176 +62,7 @@ __device__ __forceinline__ uint64_t ld40u(const uint8_t* p)
     return (uint64_t)v | ((uint64_t)b4 << 32);
 }
 
-/* workspace layout (lz4k_decode_workspace_bytes): header | nSeq[N] | fastList[N] | slowList[N] | marks[N][8192] */
-struct WsHeader { uint32_t fastCount, slowCount, fastCursor, pad; };
-
-struct WsView {
-    WsHeader* hdr; uint32_t* nSeq; uint32_t* fastList; uint32_t* slowList; uint32_t* marks;
-};
-__host__ __device__ inline WsView ws_view(void* ws, int64_t n)
-{
-    WsView v;
-    uint8_t* p = reinterpret_cast<uint8_t*>(ws);
-    v.hdr = reinterpret_cast<WsHeader*>(p); p += 256;
-    v.nSeq = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
-    v.fastList = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
-    v.slowList = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
-    v.marks = reinterpret_cast<uint32_t*>(p);
-    return v;
-}
-
-__global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
-{
-    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.nBlocks) return;
-    WsView w = ws_view(a.workspace, a.nBlocks);
-    const uint8_t* src = a.src + a.srcOff[b];
-    const int n = a.srcSize[b];
-    int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
-    uint32_t ns = 0;
-    /* the smem expand kernel takes blocks whose input and output fit its 64 KB windows */
-    const bool maybeFast = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536);
-    int r = scan_block(src, n, cap, &ns, maybeFast ? (w.marks + b * kMaxSeqFast) : nullptr);
-    a.outSize[b] = r;
-    w.nSeq[b] = ns;
-    if (r > 0) {
-        if (maybeFast && ns <= kMaxSeqFast) w.fastList[atomicAdd(&w.hdr->fastCount, 1u)] = (uint32_t)b;
-        else w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
-    }
-}
-
-#ifdef LZ4K_SCAN_V2
-/* experimental: one WARP per block (lz4_scan_v2.h); same outputs as lz4_scan_kernel */
-#include "lz4_scan_v2.h"
-__global__ void __launch_bounds__(128) lz4_scan_v2_kernel(lz4k_decode_args a)
-{
-    __shared__ SV2Shared sh[4];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t b = (int64_t)blockIdx.x * 4 + wib;
-    if (b >= a.nBlocks) return;                                       // whole warp
-    WsView w = ws_view(a.workspace, a.nBlocks);
-    const uint8_t* src = a.src + a.srcOff[b];
-    const int n = a.srcSize[b];
-    const int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
-    const bool maybeFast = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536);
-    uint32_t* marks = maybeFast ? (w.marks + b * kMaxSeqFast) : nullptr;
-    SV2Shared& S = sh[wib];
-    int r = 0;
-    uint32_t ns = 0;
-    if (cap < 64 || n < kSv2MinBytes) {
-        if (lane == 0) r = scan_block(src, n, cap, &ns, marks);
-    } else {
-        SV2Lane L;
-        sv2_phase0(lane, L, S, src, n, cap);
-        __syncwarp();
-        for (;;) {
-            sv2_decide(lane, L, S);
-            if (lane == 0) S.changed = 0;
-            __syncwarp();
-            sv2_redo(lane, L, S, src, n, cap);
-            __syncwarp();
-            const int ch = S.changed;
-            __syncwarp();
-            if (!ch) break;
-        }
-        sv2_write(lane, L, S, src, n, cap, marks);
-        __syncwarp();
-        sv2_finish(lane, S, src, n, cap, marks);
-        __syncwarp();
-        r = S.ret; ns = S.nseq;
-    }
-    if (lane == 0) {
-        a.outSize[b] = r;
-        w.nSeq[b] = ns;
-        if (r > 0) {
-            if (maybeFast && ns <= kMaxSeqFast) w.fastList[atomicAdd(&w.hdr->fastCount, 1u)] = (uint32_t)b;
-            else w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
-        }
-    }
-}
-#endif
-
-/* =============================================================================================
- * expand (generic): one warp per accepted block, any block size, straight to global memory
- * ============================================================================================= */
-__global__ void __launch_bounds__(128) lz4_expand_generic_kernel(lz4k_decode_args a)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const WsView w = ws_view(a.workspace, a.nBlocks);
-    if (idx >= (int64_t)w.hdr->slowCount) return; // only blocks the scan accepted and left to this kernel
-    const int64_t b = w.slowList[idx];
-    const uint8_t* __restrict__ src = a.src + a.srcOff[b];
-    uint8_t* dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
-    const int64_t n = a.srcSize[b];
-    int64_t ip = 0, op = 0;
-
-    for (;;) {
-        uint32_t token = ldb(src + ip); ip++;
-        int64_t ll = token >> 4;
-        if (ll == 15) { uint32_t x; do { x = ldb(src + ip); ip++; ll += x; } while (x == 255); }
-        for (int64_t k = lane; k < ll; k += 32) dst[op + k] = (uint8_t)ldb(src + ip + k);
-        ip += ll; op += ll;
-        if (ip >= n) break;
-        uint32_t offset = ld16(src + ip); ip += 2;
-        int64_t ml = token & 15;
-        if (ml == 15) { uint32_t x; do { x = ldb(src + ip); ip++; ml += x; } while (x == 255); }
-        ml += kMinMatch;
-        __syncwarp();                             // everything before `op` is now visible to all lanes
-        if (offset == 0) {                        // reference zero-fills (lz4.c:2407, :500)
-            for (int64_t k = lane; k < ml; k += 32) dst[op + k] = 0;
-        } else if ((int64_t)offset >= ml) {
-            const volatile uint8_t* from = dst + op - offset;
-            for (int64_t k = lane; k < ml; k += 32) dst[op + k] = from[k];
-        } else {                                  // self-overlapping match: period `offset`
-            const volatile uint8_t* from = dst + op - offset;
-            for (int64_t k = lane; k < ml; k += 32) dst[op + k] = from[k % offset];
-        }
-        op += ml;
-    }
-}
-
-/* =============================================================================================
- * expand (fast): one CTA per 64 KB block, everything staged in shared memory
- *
- *   TMA bulk load  : compressed block  HBM -> smem            (cp.async.bulk + mbarrier)
- *   phase A        : one LANE per sequence turns the scan's mark (token position, output position)
- *                    into an 8-byte record {matchStart, nextStart, litSrc-outStart, offset} and sets
- *                    a start bit per sequence (bit index = output position)
- *   rank           : exclusive scan of the popcounts of the start bits (sequence index of a byte =
- *                    rank of the last start bit at or before it)
- *   phase B        : output-major assembly in aligned 8-byte chunks handed out dynamically to the lanes
- *                    of a warp; one loop iteration = one piece (literal or match run clipped to the
- *                    chunk) per lane = one unaligned 8-byte smem read, masked and shifted into place;
- *                    per-chunk done flags order match reads after the writes they depend on.
- *   TMA bulk store : decoded block  smem -> HBM              (cp.async.bulk.global.shared::cta)
- * HBM traffic is exactly the algorithmic bytes (C_i in, U_i out) plus 4 bytes of marks per sequence.
- * ============================================================================================= */
-#ifndef LZ4K_FAST_THREADS
-#define LZ4K_FAST_THREADS 1024
-#endif
-constexpr int kFastThreads = LZ4K_FAST_THREADS;
-constexpr int kFastWarps = kFastThreads / 32;
-static_assert(kFastWarps == 32, "phase B's strip ownership (warp w owns strips w, w+32, ...) assumes 32 warps per CTA");
-constexpr int kInBytes = 65536 + 64;
-
-struct FastSmem {
-    alignas(16) uint8_t inPad[16];                  // reads of in[-8..-1] land here
-    alignas(16) uint8_t in[kInBytes];
-    alignas(16) uint8_t outPad[16];                 // reads of out[-4..-1] land here
-    alignas(16) uint8_t out[65536 + 16];
-    alignas(8) uint2 rec[kMaxSeqFast + 2];          // {matchStart | nextStart<<16, litDelta | offset<<16}
-    uint32_t bits[2048];                            // bit p: a sequence starts at output byte p
-    uint16_t seqbase[2048];                         // number of starts before bits[i]
-    uint32_t warpSum[32];
-    alignas(8) uint64_t mbar;
-    uint32_t nextIdx[2];                            // work-list cursor values, fetched one block ahead
-#ifdef LZ4K_PHASEB_V2
-    alignas(16) uint8_t done8[8192 + 16];           // + the always-set sentinel flag done8[kPbSentinel]
-#else
-    alignas(16) uint8_t done8[8192];                // done8[c] != 0: output bytes [8c, 8c+8) are final
-#endif
-};
+constexpr int kInBytes = 65536 + 64;           /* staged compressed block: <= 65535 bytes + 16-byte phase + rounding */
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -271,289 +99,207 @@ __device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_re
 
 
 
-/* unaligned 64-bit read from a 4-aligned shared array at byte index `idx` (>= -4) */
-__device__ __forceinline__ uint64_t lds64u(const uint8_t* base, int idx)
+/* workspace layout (lz4k_decode_workspace_bytes): header | nSeq[N] | slowList[N] | marks[N][markStride] */
+struct WsHeader { uint32_t slowCount, pad[3]; };
+
+struct WsView {
+    WsHeader* hdr; uint32_t* nSeq; uint32_t* slowList; uint32_t* marks; uint32_t markStride;
+};
+/* mark slots per block: a block the shared-memory expand kernel may take (capacity <= 64 KB) has at most
+ * capacity/4 + 1 sequences (every sequence but the last produces >= 4 bytes) and the scan visits at most one more;
+ * batches of larger blocks need no marks at all */
+__host__ __device__ inline uint32_t mark_stride(const int32_t* dstCapArr, int32_t dstCap)
 {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (idx & ~3));
-    const uint32_t sh = (uint32_t)(idx & 3) * 8u;
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+    if (dstCapArr) return (uint32_t)kMaxSeqFast;               /* per-block capacities live on the device: worst case */
+    if (dstCap <= 0 || dstCap > 65536) return 0u;
+    const uint32_t s = (uint32_t)dstCap / 4u + 2u;
+    return s < (uint32_t)kMaxSeqFast ? s : (uint32_t)kMaxSeqFast;
+}
+__host__ __device__ inline WsView ws_view(void* ws, int64_t n, uint32_t markStride)
+{
+    WsView v;
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+    v.hdr = reinterpret_cast<WsHeader*>(p); p += 256;
+    v.nSeq = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
+    v.slowList = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
+    v.marks = reinterpret_cast<uint32_t*>(p);
+    v.markStride = markStride;
+    return v;
+}
+__device__ __forceinline__ WsView ws_view(const lz4k_decode_args& a) { return ws_view(a.workspace, a.nBlocks, mark_stride(a.dstCapArr, a.dstCap)); }
+
+/* a block the shared-memory expand kernel takes: input and output fit its 64 KB windows, marks for every sequence */
+__device__ __forceinline__ bool rows_eligible(int n, int cap, uint32_t nseq, uint32_t markStride)
+{
+    return n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && nseq <= (uint32_t)kMaxSeqFast && nseq <= markStride;
 }
 
+/* ---- scan, one THREAD per block: batches of small blocks (a 4 KB block has ~150 sequences) ---- */
+__global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.nBlocks) return;
+    const WsView w = ws_view(a);
+    const uint8_t* src = a.src + a.srcOff[b];
+    const int n = a.srcSize[b];
+    int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
+    uint32_t ns = 0;
+    const bool wantMarks = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && w.markStride > 0);
+    int r = scan_block<true>(src, n, cap, &ns, wantMarks ? (w.marks + b * w.markStride) : nullptr, w.markStride);
+    a.outSize[b] = r;
+    w.nSeq[b] = ns;
+    if (r > 0 && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
+}
 
+/* ---- scan, one CTA of NL lanes per block (lz4_scan_par.h): same outputs as lz4_scan_kernel ----
+ * Blocks of up to 65 535 bytes are staged in shared memory by one TMA bulk load (the walks are chains of
+ * dependent 4-byte reads: ~30 cycles each from shared memory instead of an L2 / HBM round trip); larger
+ * blocks (lz4frame's 4 MB blocks) are walked in global memory by the same lanes. */
+#ifndef LZ4K_SCAN_LANES
+#define LZ4K_SCAN_LANES 128
+#endif
+constexpr int kScanLanes = LZ4K_SCAN_LANES;
+static_assert(kScanLanes % 32 == 0 && kScanLanes <= kSpMaxLanes, "scan lanes");
 
+struct ScanParSmem {
+    alignas(16) uint8_t in[65536 + 64];
+    SpShared sp;
+    uint32_t warpCnt[kSpMaxLanes / 32], warpLen[kSpMaxLanes / 32];
+    int first;
+    alignas(8) uint64_t mbar;
+};
 
-__global__ void __launch_bounds__(kFastThreads, 1) lz4_expand_fast_kernel(lz4k_decode_args a)
+template <bool G>
+__device__ __forceinline__ void scan_par_block(ScanParSmem& S, const uint8_t* src, int n, int cap, uint32_t* marks, uint32_t markCap,
+                                               int& ret, uint32_t& nseq)
+{
+    const int lane = threadIdx.x, nl = kScanLanes;
+    if (cap < 64 || n < kSpMinBytes) {
+        if (lane == 0) { uint32_t ns = 0; S.sp.ret = scan_block<G>(src, n, cap, &ns, marks, markCap); S.sp.nseq = ns; }
+        __syncthreads();
+        ret = S.sp.ret; nseq = S.sp.nseq;
+        __syncthreads();
+        return;
+    }
+    SpLane L;
+    sp_phase0<G>(lane, nl, L, S.sp, src, n, cap);
+    __syncthreads();
+    for (;;) {
+        sp_decide(lane, L, S.sp);
+        __syncthreads();                                   /* everybody has read S.changed's previous value and its neighbour's result */
+        if (lane == 0) S.sp.changed = 0;
+        __syncthreads();
+        sp_redo<G>(lane, L, S.sp, src, n, cap);
+        __syncthreads();
+        if (!S.sp.changed) break;
+    }
+    /* exclusive sums of (count, olen) over the lanes */
+    uint32_t c = S.sp.res[lane].count, o = S.sp.res[lane].olen, ci = c, oi = o;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t yc = __shfl_up_sync(kFull, ci, d), yo = __shfl_up_sync(kFull, oi, d);
+        if ((lane & 31) >= d) { ci += yc; oi += yo; }
+    }
+    if ((lane & 31) == 31) { S.warpCnt[lane >> 5] = ci; S.warpLen[lane >> 5] = oi; }
+    if (lane == 0) S.first = nl - 1;
+    __syncthreads();
+    uint32_t cb = ci - c, ob = oi - o;
+    for (int wq = 0; wq < (lane >> 5); wq++) { cb += S.warpCnt[wq]; ob += S.warpLen[wq]; }
+    sp_write<G>(lane, L, S.sp, src, n, cap, cb, ob, marks, markCap);
+    if (S.sp.end[lane].kind != SP_RAN) atomicMin(&S.first, lane);
+    __syncthreads();
+    sp_finish<G>(lane, S.first, S.sp, src, n, cap, marks, markCap);
+    __syncthreads();
+    ret = S.sp.ret; nseq = S.sp.nseq;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kScanLanes) lz4_scan_par_kernel(lz4k_decode_args a)
 {
     extern __shared__ __align__(16) uint8_t smemRaw[];
-    FastSmem& S = *reinterpret_cast<FastSmem*>(smemRaw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const WsView w = ws_view(a.workspace, a.nBlocks);
-    const uint32_t fastCount = w.hdr->fastCount;
+    ScanParSmem& S = *reinterpret_cast<ScanParSmem*>(smemRaw);
+    const WsView w = ws_view(a);
+    const int tid = threadIdx.x;
     uint32_t parity = 0;
-    volatile uint8_t* vDone8 = S.done8;
-
     if (tid == 0) mbar_init(&S.mbar, 1);
-#ifdef LZ4K_PHASEB_V2
-    if (tid == 0) S.done8[kPbSentinel] = 1;
-#endif
     __syncthreads();
-#ifdef LZ4K_PHASE_TIMING
-    long long tPhase = clock64();
-#endif
-
-    if (tid == 0) S.nextIdx[0] = atomicAdd(&w.hdr->fastCursor, 1u);
-    __syncthreads();
-
-    for (uint32_t it = 0;; it++) {
-        const uint32_t idx = S.nextIdx[it & 1];
-        if (idx >= fastCount) break;
-        if (tid == 0) S.nextIdx[(it + 1) & 1] = atomicAdd(&w.hdr->fastCursor, 1u);   // read after this block's barriers
-        const int64_t b = w.fastList[idx];
+    for (int64_t b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
         const uint8_t* src = a.src + a.srcOff[b];
         const int n = a.srcSize[b];
-        const int total = a.outSize[b];
-        const int nseq = (int)w.nSeq[b];
-        uint8_t* dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
-        const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
-        const uint32_t loadBytes = (uint32_t)((head + n + 15) & ~15);
-
+        const int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
+        const bool wantMarks = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && w.markStride > 0);
+        uint32_t* marks = wantMarks ? (w.marks + b * w.markStride) : nullptr;
+        int r = -1;
+        uint32_t ns = 0;
+        if (n > 0 && n <= 65535 && cap > 0) {
+            const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+            const uint32_t loadBytes = (uint32_t)((head + n + 15) & ~15);
+            if (tid == 0) {
+                mbar_expect_tx(&S.mbar, loadBytes);
+                for (uint32_t o = 0; o < loadBytes; o += 16384u)
+                    tma_load_1d(S.in + o, src - head + o, min(16384u, loadBytes - o), &S.mbar);
+            }
+            while (!mbar_try_wait(&S.mbar, parity)) { }
+            parity ^= 1;
+            scan_par_block<false>(S, S.in + head, n, cap, marks, w.markStride, r, ns);
+        } else if (n > 65535 && cap >= 64) {
+            scan_par_block<true>(S, src, n, cap, marks, w.markStride, r, ns);
+        } else {                                               /* degenerate arguments: the one-thread code decides (lz4.c:2036, :2064-2069) */
+            if (tid == 0) { uint32_t q = 0; S.sp.ret = scan_block<true>(src, n, cap, &q, nullptr, 0u); S.sp.nseq = q; }
+            __syncthreads();
+            r = S.sp.ret; ns = S.sp.nseq;
+            __syncthreads();
+        }
         if (tid == 0) {
-            mbar_expect_tx(&S.mbar, loadBytes);
-            for (uint32_t o = 0; o < loadBytes; o += 16384u)
-                tma_load_1d(S.in + o, src - head + o, min(16384u, loadBytes - o), &S.mbar);
+            a.outSize[b] = r;
+            w.nSeq[b] = ns;
+            if (r > 0 && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
         }
-        for (int k = tid; k < 2048; k += kFastThreads) S.bits[k] = 0;
-        for (int k = tid; k < 1024; k += kFastThreads) reinterpret_cast<uint64_t*>(S.done8)[k] = 0;
-        __syncthreads();
-        /* this thread's first sequence marks (phase A), fetched while the TMA load is in flight */
-        const uint32_t* marks = w.marks + b * kMaxSeqFast;
-        uint32_t mark0 = 0, mark1 = 0;                         // marks[tid], marks[tid + 1]
-        if (tid < nseq) mark0 = marks[tid];
-        if (tid + 1 < nseq) mark1 = marks[tid + 1];
-        PHASE_MARK(0);                                     // fetch + zeroing
-        while (!mbar_try_wait(&S.mbar, parity)) { }
-        parity ^= 1;
-        PHASE_MARK(1);                                     // TMA load wait
-
-        /* ---- phase A: sequence records + start bits, one lane per sequence ----
-         * mark k = (token position, output start) of sequence k; the next mark's output start is where
-         * sequence k ends.  The lane re-reads only its own token: literal length (with extension
-         * bytes), offset; the match length follows from the two output positions. */
-        const uint8_t* in = S.in + head;
-        for (int k = tid; k < nseq; k += kFastThreads) {
-            const uint32_t mk = (k == tid) ? mark0 : marks[k];
-            const bool last = (k + 1 == nseq);
-            const uint32_t mkn = last ? 0u : ((k == tid) ? mark1 : marks[k + 1]);
-            const int tok = (int)(mk & 0xFFFFu);
-            int op = (int)(mk >> 16);
-            if (k != 0 && op == 0) op = 65536;                 // only an empty final sequence can start at 65536
-            int nxt = last ? total : (int)(mkn >> 16);
-            if (!last && nxt == 0) nxt = 65536;
-            const uint32_t t = in[tok];
-            int pp = tok + 1;
-            int ll = (int)(t >> 4);
-            if (ll == 15) { uint32_t x; do { x = in[pp++]; ll += (int)x; } while (x == 255); }
-            const int ls = pp;                                 // first literal byte in the input
-            uint32_t off = 0;
-            if (!last) off = (uint32_t)in[pp + ll] | ((uint32_t)in[pp + ll + 1] << 8);
-            if (op < total) atomicOr(&S.bits[op >> 5], 1u << (op & 31));
-            /* record: {matchStart | nextStart<<16, (litSrc-outStart)&0xFFFF | offset<<16} */
-            S.rec[k] = make_uint2(((uint32_t)(op + ll) & 0xFFFFu) | ((uint32_t)nxt << 16),
-                                  ((uint32_t)(ls - op) & 0xFFFFu) | (off << 16));
-        }
-        __syncthreads();
-        PHASE_MARK(2);                                     // phase A
-
-        /* ---- rank: seqbase[i] = number of start bits in bits[0..i) ---- */
-        {
-            constexpr int WPT = 2048 / kFastThreads;
-            uint32_t cnt[WPT], x = 0;
-            #pragma unroll
-            for (int j = 0; j < WPT; j++) { cnt[j] = __popc(S.bits[tid * WPT + j]); x += cnt[j]; }
-            uint32_t incl = x;
-            #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += y; }
-            if (lane == 31) S.warpSum[warp] = incl;
-            __syncthreads();
-            if (warp == 0) {
-                uint32_t v = (lane < kFastWarps) ? S.warpSum[lane] : 0;
-                #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, v, d); if (lane >= d) v += y; }
-                S.warpSum[lane] = v;
-            }
-            __syncthreads();
-            uint32_t ex = incl - x + (warp ? S.warpSum[warp - 1] : 0);
-            #pragma unroll
-            for (int j = 0; j < WPT; j++) { S.seqbase[tid * WPT + j] = (uint16_t)ex; ex += cnt[j]; }
-            PHASE_MARK(3);                                 // rank
-            if (tid == 0) tma_wait_read0();        // previous block's bulk store has finished reading S.out
-            PHASE_MARK(4);                                 // wait for previous store
-        }
-        __syncthreads();
-
-        /* ---- phase B: assemble the output in aligned 8-byte chunks ----
-         * Warp w owns the 256-byte strips w, w+32, w+64, ...: at any moment the CTA works on an
-         * 8 KB window that slides forward, so almost all match sources are final long before they
-         * are needed.  Inside a warp the chunks of its strips are handed out DYNAMICALLY: a lane that
-         * finishes a chunk takes the warp's next one (ballot + popcount ranking), so lanes whose
-         * chunks hold many tiny pieces do not hold the others back.  The loop is flattened: one
-         * iteration handles one PIECE (literal run or match run clipped to the chunk) per lane --
-         * one unaligned 8-byte read from the staged input (literals) or the output window (match),
-         * masked and shifted into place.  A match piece whose source chunks are not flagged done
-         * simply does not advance in this iteration (no spin loops, no warp-level barriers). */
-#ifdef LZ4K_PHASEB_V2
-        {   /* experimental: same hand-out and flag protocol, one code path for literal and match pieces */
-            const int nstrips = (total + 255) >> 8;
-            const int warpChunks = (warp < nstrips) ? (((nstrips - 1 - warp) >> 5) + 1) << 5 : 0;
-            int warpNext = 0;
-            PBView V;
-            V.window = S.in; V.out = S.out; V.outDelta = (int)(S.out - S.in);
-            V.rec = reinterpret_cast<const pb_rec*>(S.rec); V.bits = S.bits; V.seqbase = S.seqbase;
-            V.done8 = S.done8; V.head = head; V.total = total;
-            PBLane L;
-            pb_init(L);
-            for (;;) {
-                const unsigned want = __ballot_sync(kFull, L.needNew && !L.exhausted);
-                if (want) {
-                    const int c = warpNext + __popc(want & ((1u << lane) - 1u));
-                    warpNext += __popc(want);
-                    if (L.needNew && !L.exhausted) pb_take(L, V, warp, c, warpChunks);
-                }
-                const unsigned act = __ballot_sync(kFull, !L.needNew);
-                if (act == 0u) {
-                    if (__ballot_sync(kFull, !L.exhausted) == 0u) break;
-                    continue;
-                }
-                if (!L.needNew) pb_body(L, V);
-            }
-        }
-#else
-        {
-            const int nstrips = (total + 255) >> 8;
-            const int warpChunks = (warp < nstrips) ? (((nstrips - 1 - warp) >> 5) + 1) << 5 : 0;   // chunks in this warp's strips
-            int warpNext = 0;                                  // next chunk (of this warp's list) to hand out; warp-uniform
-            bool needNew = true, exhausted = false;
-            int p = 0, pe = 0, k = 0, m = 0, e = 0, off = 0, pos = 0;
-            uint32_t d = 0;
-            uint64_t acc = 0;
-#ifdef LZ4K_PHASE_TIMING
-            unsigned statIter = 0, statLane = 0, statBlocked = 0;
-#endif
-            for (;;) {
-                const unsigned want = __ballot_sync(kFull, needNew && !exhausted);
-                if (want) {
-                    const int c = warpNext + __popc(want & ((1u << lane) - 1u));
-                    warpNext += __popc(want);
-                    if (needNew && !exhausted) {
-                        if (c >= warpChunks) {
-                            exhausted = true;
-                        } else {
-                            p = ((warp + ((c >> 5) << 5)) << 8) + ((c & 31) << 3);
-                            if (p < total) {                   // (chunks past the end of the block are skipped)
-                                pe = min(p + 8, total);
-                                const uint32_t bw = S.bits[p >> 5];
-                                k = (int)S.seqbase[p >> 5] + __popc(bw & (0xFFFFFFFFu >> (31 - (p & 31)))) - 1;
-                                const uint2 r = S.rec[k];
-                                m = (int)(r.x & 0xFFFFu); e = (int)(r.x >> 16); off = (int)(r.y >> 16);
-                                d = r.y & 0xFFFFu;
-                                if (m == 0 && k != 0) m = 65536;   // 16-bit wrap of 65536
-                                if (e == 0) e = 65536;
-                                pos = p; acc = 0;
-                                needNew = false;
-                            }
-                        }
-                    }
-                }
-                const unsigned act = __ballot_sync(kFull, !needNew);   // lanes holding a chunk
-                if (act == 0u) {
-                    if (__ballot_sync(kFull, !exhausted) == 0u) break;     // nothing in flight, nothing left to hand out
-                    continue;
-                }
-#ifdef LZ4K_PHASE_TIMING
-                statIter++;
-                statLane += __popc(act);
-#endif
-                if (!needNew) {
-                    bool ok = true;
-                    uint64_t v = 0;
-                    int end;
-                    if (pos < m) {                             // literal piece
-                        end = min(m, pe);
-                        v = lds64u(S.in, head + (int)((pos + d) & 0xFFFFu));
-                    } else {                                   // match piece
-                        end = min(e, pe);
-                        if (off >= 8) {
-                            const int src = pos - off;
-                            ok = (vDone8[src >> 3] & vDone8[(end - 1 - off) >> 3]) != 0;
-                            if (ok) { fence_acq_rel_cta(); v = lds64u(S.out, src); }   // flags before data
-                        } else if (off != 0) {                 // short period or source inside this chunk
-                            #pragma unroll 1
-                            for (int x = pos; x < end; x++) {
-                                int sidx = x - off;
-                                if (sidx >= m) sidx = m - off + ((x - m) % off);       // always before the match
-                                uint32_t byte;
-                                if (sidx >= p) {
-                                    byte = (uint32_t)((acc >> (8 * (sidx - p))) & 0xFFu);
-                                } else {
-                                    if (!vDone8[sidx >> 3]) { ok = false; break; }
-                                    fence_acq_rel_cta();
-                                    byte = S.out[sidx];
-                                }
-                                v |= (uint64_t)byte << (8 * (x - pos));
-                            }
-                        }                                      // off == 0: zero bytes (lz4.c:2407)
-                    }
-                    __syncwarp(act);                           // literal and match lanes rejoin: the tail below runs once
-#ifdef LZ4K_PHASE_TIMING
-                    if (!ok) statBlocked++;
-#endif
-                    if (ok) {
-                        const int len = end - pos;
-                        v &= 0xFFFFFFFFFFFFFFFFull >> (64 - 8 * len);
-                        acc |= v << (8 * (pos - p));
-                        pos = end;
-                        if (pos >= pe) {                       // chunk complete: publish it
-                            *reinterpret_cast<uint64_t*>(S.out + p) = acc;
-                            fence_acq_rel_cta();               // data before flag
-                            vDone8[p >> 3] = 1;
-                            needNew = true;
-                        } else if (pos == e) {                 // next sequence starts inside this chunk
-                            k++;
-                            const uint2 r = S.rec[k];
-                            m = (int)(r.x & 0xFFFFu); e = (int)(r.x >> 16); off = (int)(r.y >> 16);
-                            d = r.y & 0xFFFFu;
-                            if (m == 0) m = 65536;
-                            if (e == 0) e = 65536;
-                        }
-                    }
-                }
-            }
-#ifdef LZ4K_PHASE_TIMING
-            if (lane == 0) { atomicAdd(&g_loopStats[0], (unsigned long long)statIter); atomicAdd(&g_loopStats[1], (unsigned long long)statLane); }
-            atomicAdd(&g_loopStats[2], (unsigned long long)statBlocked);
-#endif
-        }
-#endif  /* LZ4K_PHASEB_V2 */
-        __syncthreads();
-        PHASE_MARK(5);                                     // phase B
-
-        /* ---- store: smem -> HBM ---- */
-        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-            fence_proxy_async();
-            __syncthreads();
-            const uint32_t bulk = (uint32_t)total & ~15u;
-            if (tid == 0 && bulk) {
-                for (uint32_t o = 0; o < bulk; o += 16384u) tma_store_1d(dst + o, S.out + o, min(16384u, bulk - o));
-                tma_commit();
-            }
-            if (tid < (total & 15)) dst[bulk + tid] = S.out[bulk + tid];
-        } else {
-            for (int k = tid; k < total; k += kFastThreads) dst[k] = S.out[k];
-        }
-        PHASE_MARK(6);                                     // store issue
     }
-    if (tid == 0) tma_wait_all0();
+}
+
+/* =============================================================================================
+ * expand (generic): one warp per accepted block, any block size, straight to global memory
+ * ============================================================================================= */
+__global__ void __launch_bounds__(128) lz4_expand_generic_kernel(lz4k_decode_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const WsView w = ws_view(a);
+    const int64_t count = w.hdr->slowCount;       // only blocks the scan accepted and left to this kernel
+    for (int64_t idx = warp0; idx < count; idx += nWarps) {
+    const int64_t b = w.slowList[idx];
+    const uint8_t* __restrict__ src = a.src + a.srcOff[b];
+    uint8_t* dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
+    const int64_t n = a.srcSize[b];
+    int64_t ip = 0, op = 0;
+
+    for (;;) {
+        uint32_t token = ldb<true>(src + ip); ip++;
+        int64_t ll = token >> 4;
+        if (ll == 15) { uint32_t x; do { x = ldb<true>(src + ip); ip++; ll += x; } while (x == 255); }
+        for (int64_t k = lane; k < ll; k += 32) dst[op + k] = (uint8_t)ldb<true>(src + ip + k);
+        ip += ll; op += ll;
+        if (ip >= n) break;
+        uint32_t offset = ld16<true>(src + ip); ip += 2;
+        int64_t ml = token & 15;
+        if (ml == 15) { uint32_t x; do { x = ldb<true>(src + ip); ip++; ml += x; } while (x == 255); }
+        ml += kMinMatch;
+        __syncwarp();                             // everything before `op` is now visible to all lanes
+        if (offset == 0) {                        // reference zero-fills (lz4.c:2407, :500)
+            for (int64_t k = lane; k < ml; k += 32) dst[op + k] = 0;
+        } else if ((int64_t)offset >= ml) {
+            const volatile uint8_t* from = dst + op - offset;
+            for (int64_t k = lane; k < ml; k += 32) dst[op + k] = from[k];
+        } else {                                  // self-overlapping match: period `offset`
+            const volatile uint8_t* from = dst + op - offset;
+            for (int64_t k = lane; k < ml; k += 32) dst[op + k] = from[k % offset];
+        }
+        op += ml;
+    }
+    __syncwarp();
+    }
 }
 
 /* =============================================================================================
@@ -577,6 +323,13 @@ constexpr int kRowsRpt = LZ4K_ROWS_RPT;
 constexpr int kWave = kRowsThreads * kRowsRpt;
 constexpr int kRowsCache = 3;                /* sequences per thread whose parse is kept in registers between the passes */
 
+struct RowsDesc {                            /* one block's arguments, fetched a block ahead */
+    const uint8_t* src;
+    uint8_t* dst;
+    int n, total, nseq;
+    int64_t b;
+};
+
 struct RowsSmem {
     alignas(16) uint8_t zero[16];            /* always-zero cell: source of offset-0 matches (lz4.c:2407) */
     alignas(16) uint8_t in[kInBytes];        /* staged compressed block; keeps the source's 16-byte phase */
@@ -584,8 +337,9 @@ struct RowsSmem {
     alignas(16) uint32_t tab[kRowsMaxRuns];  /* delta per run */
     alignas(8) uint2 rows[2048];             /* {run-start bits of the row, run starts before the row - 1} */
     uint32_t warpSum[32];
-    alignas(8) uint64_t mbar;
-    uint32_t nextIdx[2];
+    alignas(8) uint64_t mbar;                /* TMA load of `in` */
+    alignas(8) uint64_t wbar;                /* wave barrier: one arrival per warp */
+    RowsDesc desc[2];
     uint32_t nRuns;
 };
 static_assert(sizeof(RowsSmem) <= 232448, "RowsSmem exceeds the 227 KB of shared memory a CTA can opt in to");
@@ -605,13 +359,18 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a)
 {
     uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v)
 {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t lanemask_le()
 {
@@ -620,30 +379,31 @@ __device__ __forceinline__ uint32_t lanemask_le()
     return m;
 }
 
-/* One wave of the rows kernel for one thread: bytes p0 + r*1024 (r < kRowsRpt) of the wave that starts at shared
+/* Source addresses of one thread's bytes of a wave: bytes p0 + r*1024 (r < kRowsRpt) of the wave that starts at shared
  * address waveS.  FULL: the whole wave lies inside the block (no bounds checks).  All addresses are 32-bit
- * shared-window addresses; every load of the wave is issued before its first store. */
+ * shared-window addresses.  Nothing here reads the output window: the run table alone decides where a byte comes
+ * from, so a warp resolves wave w+1 while other warps still copy wave w. */
 template <bool FULL>
-__device__ __forceinline__ void rows_wave(const uint32_t p0, const uint32_t waveS, const uint32_t lim, const uint32_t outS,
-                                          const uint32_t rowsS, const uint32_t tabS, const uint32_t zeroS, const uint32_t le)
+__device__ __forceinline__ void rows_resolve(uint32_t (&sa)[LZ4K_ROWS_RPT], const uint32_t p0, const uint32_t waveS,
+                                             const uint32_t lim, const uint32_t outS, const uint32_t rowsS,
+                                             const uint32_t tabS, const uint32_t zeroS, const uint32_t le)
 {
     const uint32_t rowAddr = rowsS + ((p0 >> 5) << 3);
-    uint32_t sa[kRowsRpt];                                     /* shared address of each byte's source */
     #pragma unroll
-    for (int r = 0; r < kRowsRpt; r++) {
+    for (int r = 0; r < LZ4K_ROWS_RPT; r++) {
         sa[r] = zeroS;
-        if (FULL || p0 + (uint32_t)(r * kRowsThreads) < lim) {
-            const uint2 row = lds_u64(rowAddr + (uint32_t)(r * (kRowsThreads / 32) * 8));
+        if (FULL || p0 + (uint32_t)(r * 1024) < lim) {
+            const uint2 row = lds_u64(rowAddr + (uint32_t)(r * 32 * 8));
             const uint32_t j = row.y + (uint32_t)__popc(row.x & le);
-            sa[r] = outS + p0 + (uint32_t)(r * kRowsThreads) + lds_u32(tabS + (j << 2));
+            sa[r] = outS + p0 + (uint32_t)(r * 1024) + lds_u32(tabS + (j << 2));
         }
     }
     uint32_t hi = sa[0];
     #pragma unroll
-    for (int r = 1; r < kRowsRpt; r++) hi = max(hi, sa[r]);
+    for (int r = 1; r < LZ4K_ROWS_RPT; r++) hi = max(hi, sa[r]);
     if (hi >= waveS) {                                         /* sources inside this wave: follow them */
         #pragma unroll
-        for (int r = 0; r < kRowsRpt; r++) {
+        for (int r = 0; r < LZ4K_ROWS_RPT; r++) {
             uint32_t x = sa[r];
             while (x >= waveS) {
                 const uint32_t q = x - outS;
@@ -654,59 +414,78 @@ __device__ __forceinline__ void rows_wave(const uint32_t p0, const uint32_t wave
             sa[r] = x;
         }
     }
-    uint32_t v[kRowsRpt];
-    #pragma unroll
-    for (int r = 0; r < kRowsRpt; r++) v[r] = lds_u8(sa[r]);
-    #pragma unroll
-    for (int r = 0; r < kRowsRpt; r++)
-        if (FULL || p0 + (uint32_t)(r * kRowsThreads) < lim) sts_u8(outS + p0 + (uint32_t)(r * kRowsThreads), v[r]);
 }
 
 __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_decode_args a)
 {
+    static_assert(kRowsThreads == 1024, "rows_resolve assumes 1024 threads (32 rows per wave slice)");
     extern __shared__ __align__(16) uint8_t smemRaw[];
     RowsSmem& S = *reinterpret_cast<RowsSmem*>(smemRaw);
-    uint8_t* const win = smemRaw;                               /* the window: one byte array over the whole struct */
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const WsView w = ws_view(a.workspace, a.nBlocks);
-    const uint32_t fastCount = w.hdr->fastCount;
+    const WsView w = ws_view(a);
     const uint32_t le = lanemask_le();
     const uint32_t outA = (uint32_t)offsetof(RowsSmem, out);
     const int zeroDelta0 = (int)offsetof(RowsSmem, zero) - (int)outA;
     const uint32_t sBase = smem_u32(smemRaw);
     const uint32_t outS = sBase + outA, zeroS = sBase + (uint32_t)offsetof(RowsSmem, zero);
     const uint32_t rowsS = sBase + (uint32_t)offsetof(RowsSmem, rows), tabS = sBase + (uint32_t)offsetof(RowsSmem, tab);
-    uint32_t parity = 0;
+    uint32_t parity = 0, wpar = 0;
 
-    if (tid == 0) mbar_init(&S.mbar, 1);
+    /* a block's arguments; n = 0 marks "nothing to do here" (past the end, rejected by the scan, or a block of the
+     * generic kernel: input > 65535 bytes, capacity > 64 KB, more than kMaxSeqFast sequences) */
+    auto fetch = [&](int64_t b) {
+        RowsDesc d;
+        d.b = b; d.src = nullptr; d.dst = nullptr; d.n = 0; d.total = 0; d.nseq = 0;
+        if (b < a.nBlocks) {
+            const int n = a.srcSize[b], total = a.outSize[b];
+            const int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
+            const uint32_t ns = w.nSeq[b];
+            if (total > 0 && rows_eligible(n, cap, ns, w.markStride)) {
+                d.src = a.src + a.srcOff[b];
+                d.dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
+                d.n = n; d.total = total; d.nseq = (int)ns;
+            }
+        }
+        return d;
+    };
+    auto issueLoad = [&](const RowsDesc& d) {                     /* thread 0: TMA bulk load of the compressed block */
+        const int head = (int)(reinterpret_cast<uintptr_t>(d.src) & 15);
+        const uint32_t loadBytes = (uint32_t)((head + d.n + 15) & ~15);
+        mbar_expect_tx(&S.mbar, loadBytes);
+        for (uint32_t o = 0; o < loadBytes; o += 16384u)
+            tma_load_1d(S.in + o, d.src - head + o, min(16384u, loadBytes - o), &S.mbar);
+    };
+
+    if (tid == 0) { mbar_init(&S.mbar, 1); mbar_init(&S.wbar, kRowsThreads / 32); }
     if (tid < 4) reinterpret_cast<uint32_t*>(S.zero)[tid] = 0;
-    if (tid == 0) S.nextIdx[0] = atomicAdd(&w.hdr->fastCursor, 1u);
+    if (tid == 0) {
+        S.desc[0] = fetch(blockIdx.x);
+        if (S.desc[0].n > 0) issueLoad(S.desc[0]);
+    }
     __syncthreads();
 #ifdef LZ4K_PHASE_TIMING
     long long tPhase = clock64();
 #endif
 
+    /* static assignment: CTA c takes blocks c, c + grid, c + 2 grid, ... (blocks of a batch cost about the same) */
     for (uint32_t it = 0;; it++) {
-        const uint32_t idx = S.nextIdx[it & 1];
-        if (idx >= fastCount) break;
-        if (tid == 0) S.nextIdx[(it + 1) & 1] = atomicAdd(&w.hdr->fastCursor, 1u);   // read after this block's barriers
-        const int64_t b = w.fastList[idx];
-        const uint8_t* src = a.src + a.srcOff[b];
-        const int n = a.srcSize[b];
-        const int total = a.outSize[b];
-        const int nseq = (int)w.nSeq[b];
-        uint8_t* dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
-        const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
-        const uint32_t loadBytes = (uint32_t)((head + n + 15) & ~15);
-
-        if (tid == 0) {
-            mbar_expect_tx(&S.mbar, loadBytes);
-            for (uint32_t o = 0; o < loadBytes; o += 16384u)
-                tma_load_1d(S.in + o, src - head + o, min(16384u, loadBytes - o), &S.mbar);
+        const int64_t b = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+        if (b >= a.nBlocks) break;
+        const RowsDesc d = S.desc[it & 1];
+        RowsDesc dn;                                           /* the next block's arguments: loads issued now, used after the waves */
+        if (tid == 0) dn = fetch(b + gridDim.x);
+        if (d.n == 0) {                                        /* not a block of this kernel */
+            __syncthreads();
+            if (tid == 0) { S.desc[(it + 1) & 1] = dn; if (dn.n > 0) issueLoad(dn); }
+            __syncthreads();
+            continue;
         }
+        const int n = d.n, total = d.total, nseq = d.nseq;
+        const int head = (int)(reinterpret_cast<uintptr_t>(d.src) & 15);
+
         for (int k = tid; k < 2048; k += kRowsThreads) S.rows[k] = make_uint2(0u, 0u);
         /* this thread's first marks, fetched while the TMA load is in flight */
-        const uint32_t* marks = w.marks + b * kMaxSeqFast;
+        const uint32_t* marks = w.marks + d.b * w.markStride;
         uint32_t mk[kRowsCache], mkn[kRowsCache];
         #pragma unroll
         for (int i = 0; i < kRowsCache; i++) {
@@ -715,7 +494,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
             mkn[i] = (k + 1 < nseq) ? marks[k + 1] : 0u;
         }
         __syncthreads();                                   /* rows are zero */
-        PHASE_MARK(0);                                     // fetch + zeroing
+        PHASE_MARK(0);                                     // zeroing + marks
         while (!mbar_try_wait(&S.mbar, parity)) { }
         parity ^= 1;
         PHASE_MARK(1);                                     // TMA load wait
@@ -751,13 +530,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
             for (int j = 0; j < WPT; j++) { cnt[j] = __popc(S.rows[tid * WPT + j].x); x += cnt[j]; }
             uint32_t incl = x;
             #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += y; }
+            for (int dd = 1; dd < 32; dd <<= 1) { uint32_t y = __shfl_up_sync(kFull, incl, dd); if (lane >= dd) incl += y; }
             if (lane == 31) S.warpSum[warp] = incl;
             __syncthreads();
             if (warp == 0) {
                 uint32_t v = S.warpSum[lane];
                 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, v, d); if (lane >= d) v += y; }
+                for (int dd = 1; dd < 32; dd <<= 1) { uint32_t y = __shfl_up_sync(kFull, v, dd); if (lane >= dd) v += y; }
                 S.warpSum[lane] = v;
                 if (lane == 31) S.nRuns = v;
             }
@@ -770,18 +549,16 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
         if (tid == 0) tma_wait_read0();                    /* the previous block's bulk store has finished reading S.out */
         __syncthreads();
         PHASE_MARK(3);                                     // rank
-        if (nRuns > (uint32_t)kRowsMaxRuns) {              /* (pathological) too many runs for the table: generic kernel */
-            if (tid == 0) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
-            continue;
-        }
+        const bool tooMany = nRuns > (uint32_t)kRowsMaxRuns;   /* (pathological) more runs than the table holds: generic kernel */
+        if (tooMany && tid == 0) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)d.b;
 
-        /* ---- runs, pass 2: delta of every run at its rank ---- */
-        {
+        if (!tooMany) {
+            /* ---- runs, pass 2: delta of every run at its rank ---- */
             auto emit = [&](const RwSeq& s) {
                 if (s.ll > 0) S.tab[rw_rank(S.rows, (uint32_t)s.op)] = (inA + (uint32_t)s.ls) - (outA + (uint32_t)s.op);
                 if (s.mlen > 0) {
                     uint32_t j = rw_rank(S.rows, (uint32_t)s.m);
-                    rw_match_runs(s.m, s.off, s.mlen, zeroDelta0, [&](int, int d) { S.tab[j++] = (uint32_t)d; });
+                    rw_match_runs(s.m, s.off, s.mlen, zeroDelta0, [&](int, int dlt) { S.tab[j++] = (uint32_t)dlt; });
                 }
             };
             #pragma unroll
@@ -793,34 +570,58 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
                 const bool last = (k + 1 == nseq);
                 emit(rw_parse(in, marks[k], last ? 0u : marks[k + 1], k, last, total));
             }
-        }
-        __syncthreads();
-        PHASE_MARK(4);                                     // pass 2
+            __syncthreads();
+            PHASE_MARK(4);                                     // pass 2
 
-        /* ---- waves ---- */
-        {
+            /* ---- waves: resolve (run table only) | wait for the previous wave | copy | arrive ---- */
             const int nWaves = (total + kWave - 1) / kWave;
-            for (int wv = 0; wv < nWaves; wv++) {
+            uint32_t sa[kRowsRpt];
+            auto resolve = [&](int wv) {
                 const uint32_t p0 = (uint32_t)(wv * kWave + tid);
-                if ((wv + 1) * kWave <= total) rows_wave<true>(p0, outS + (uint32_t)(wv * kWave), 0xFFFFFFFFu, outS, rowsS, tabS, zeroS, le);
-                else rows_wave<false>(p0, outS + (uint32_t)(wv * kWave), (uint32_t)total, outS, rowsS, tabS, zeroS, le);
-                if (wv == nWaves - 1) fence_proxy_async();  /* generic-proxy writes of `out` before the bulk store reads them */
-                __syncthreads();
+                if ((wv + 1) * kWave <= total) rows_resolve<true>(sa, p0, outS + (uint32_t)(wv * kWave), 0xFFFFFFFFu, outS, rowsS, tabS, zeroS, le);
+                else rows_resolve<false>(sa, p0, outS + (uint32_t)(wv * kWave), (uint32_t)total, outS, rowsS, tabS, zeroS, le);
+            };
+            resolve(0);
+            for (int wv = 0; wv < nWaves; wv++) {
+                if (wv > 0) { while (!mbar_try_wait(&S.wbar, wpar)) { } wpar ^= 1; }   /* every warp has copied wave wv-1 */
+                const uint32_t p0 = (uint32_t)(wv * kWave + tid);
+                const uint32_t lim = ((wv + 1) * kWave <= total) ? 0xFFFFFFFFu : (uint32_t)total;
+                uint32_t v[kRowsRpt];
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++) v[r] = lds_u8(sa[r]);
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++)
+                    if (p0 + (uint32_t)(r * kRowsThreads) < lim) sts_u8(outS + p0 + (uint32_t)(r * kRowsThreads), v[r]);
+                if (wv == nWaves - 1) fence_proxy_async();     /* generic-proxy writes of `out` before the bulk store reads them */
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.wbar);           /* release: this warp's bytes of wave wv are written */
+                if (wv + 1 < nWaves) resolve(wv + 1);
             }
+            while (!mbar_try_wait(&S.wbar, wpar)) { }
+            wpar ^= 1;
+            PHASE_MARK(5);                                     // waves
         }
-        PHASE_MARK(5);                                     // waves
 
-        /* ---- store: smem -> HBM ---- */
-        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-            const uint32_t bulk = (uint32_t)total & ~15u;
-            if (tid == 0 && bulk) {
-                for (uint32_t o = 0; o < bulk; o += 16384u) tma_store_1d(dst + o, S.out + o, min(16384u, bulk - o));
-                tma_commit();
-            }
-            if (tid < (total & 15)) dst[bulk + tid] = S.out[bulk + tid];
-        } else {
-            for (int k = tid; k < total; k += kRowsThreads) dst[k] = S.out[k];
+        /* `in`, `tab` and `rows` are dead: start the next block's load before anything else */
+        if (tid == 0) {
+            S.desc[(it + 1) & 1] = dn;
+            if (dn.n > 0) issueLoad(dn);
         }
+        /* ---- store: smem -> HBM ---- */
+        if (!tooMany) {
+            uint8_t* dst = d.dst;
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                const uint32_t bulk = (uint32_t)total & ~15u;
+                if (tid == 0 && bulk) {
+                    for (uint32_t o = 0; o < bulk; o += 16384u) tma_store_1d(dst + o, S.out + o, min(16384u, bulk - o));
+                    tma_commit();
+                }
+                if (tid < (total & 15)) dst[bulk + tid] = S.out[bulk + tid];
+            } else {
+                for (int k = tid; k < total; k += kRowsThreads) dst[k] = S.out[k];
+            }
+        }
+        __syncthreads();                                   /* desc[(it+1)&1] is visible; `out` tail reads are done */
         PHASE_MARK(6);                                     // store issue
     }
     if (tid == 0) tma_wait_all0();
@@ -833,8 +634,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
 template <bool SMALL> struct Table;
 template <> struct Table<true> {       // byU16, 13-bit 4-byte hash (lz4.c:779-780)
     uint16_t* t;
-    __device__ __forceinline__ uint32_t hash(const uint8_t* p) const { return (ld32u(p) * 2654435761u) >> 19; }
-    __device__ __forceinline__ uint32_t hashv(const uint8_t* p, uint32_t& v32) const { v32 = ld32u(p); return (v32 * 2654435761u) >> 19; }
+    __device__ __forceinline__ uint32_t hash(const uint8_t* p) const { return (ld32u<true>(p) * 2654435761u) >> 19; }
+    __device__ __forceinline__ uint32_t hashv(const uint8_t* p, uint32_t& v32) const { v32 = ld32u<true>(p); return (v32 * 2654435761u) >> 19; }
     __device__ __forceinline__ uint32_t get(uint32_t h) const { return t[h]; }
     __device__ __forceinline__ void put(uint32_t h, uint32_t pos) const { t[h] = (uint16_t)pos; }
 };
@@ -908,7 +709,7 @@ __device__ int encode_block(const uint8_t* __restrict__ src, const int n, uint8_
                 const uint32_t c = lower ? pPrev : old;       // table value this visit would read
                 bool hit = false;
                 if (!term) {
-                    if (SMALL || c + kMaxDistance >= p) hit = (ld32u(src + c) == v32);   // lz4.c:1090-1096
+                    if (SMALL || c + kMaxDistance >= p) hit = (ld32u<true>(src + c) == v32);   // lz4.c:1090-1096
                 }
                 const unsigned termMask = __ballot_sync(kFull, term);
                 const unsigned hitMask = __ballot_sync(kFull, hit);
@@ -938,7 +739,7 @@ __device__ int encode_block(const uint8_t* __restrict__ src, const int n, uint8_
         for (;;) {
             const uint32_t room = min(ip - anchor, cand);
             const uint32_t k = lane + 1;
-            const bool eq = (k <= room) && (ldb(src + ip - k) == ldb(src + cand - k));
+            const bool eq = (k <= room) && (ldb<true>(src + ip - k) == ldb<true>(src + cand - k));
             const unsigned m = __ballot_sync(kFull, eq);
             const uint32_t run = (m == kFull) ? 32u : (uint32_t)(__ffs(~m) - 1);
             ip -= run; cand -= run;
@@ -957,7 +758,7 @@ __device__ int encode_block(const uint8_t* __restrict__ src, const int n, uint8_
                     const uint32_t lim = matchlimit - (ip + kMinMatch);    // bytes comparable
                     for (uint32_t base = 0;; base += 32) {
                         const uint32_t k = base + lane;
-                        const bool eq = (k < lim) && (ldb(pa + k) == ldb(pb + k));
+                        const bool eq = (k < lim) && (ldb<true>(pa + k) == ldb<true>(pb + k));
                         const unsigned m = __ballot_sync(kFull, eq);
                         if (m != kFull) { mcode = base + (uint32_t)(__ffs(~m) - 1); break; }
                     }
@@ -968,7 +769,7 @@ __device__ int encode_block(const uint8_t* __restrict__ src, const int n, uint8_
                     /* lz4.c:1114-1117 */
                     if (limited && (int64_t)o + lit + (2 + 1 + kLastLiterals) + lit / 255 > olimit) return 0;
                     if (lit >= 15) o = emit_runlength(dst, o, lit - 15, lane);
-                    for (uint32_t k = lane; k < lit; k += 32) dst[o + k] = (uint8_t)ldb(src + anchor + k);
+                    for (uint32_t k = lane; k < lit; k += 32) dst[o + k] = (uint8_t)ldb<true>(src + anchor + k);
                     o += lit;
                 }
                 /* offset, lz4.c:1162 */
@@ -997,7 +798,7 @@ __device__ int encode_block(const uint8_t* __restrict__ src, const int n, uint8_
                     __syncwarp();
                     if (lane == 0) T.put(h, ip);
                     __syncwarp();
-                    if ((SMALL || cand + kMaxDistance >= ip) && ld32u(src + cand) == v32) {
+                    if ((SMALL || cand + kMaxDistance >= ip) && ld32u<true>(src + cand) == v32) {
                         haveLiterals = false; lit = 0;
                         continue;
                     }
@@ -1015,7 +816,7 @@ tail:   /* lz4.c:1302-1329 */
         uint32_t o = op + 1;
         if (lane == 0) dst[op] = (uint8_t)(min(last, 15u) << 4);
         if (last >= 15) o = emit_runlength(dst, o, last - 15, lane);
-        for (uint32_t k = lane; k < last; k += 32) dst[o + k] = (uint8_t)ldb(src + anchor + k);
+        for (uint32_t k = lane; k < last; k += 32) dst[o + k] = (uint8_t)ldb<true>(src + anchor + k);
         return (int)(o + last);
     }
 }
@@ -1137,51 +938,64 @@ int lz4k_debug_phase_cycles(unsigned long long* out8)   /* out8: 12 values (8 ph
     return (int)e;
 }
 
-size_t lz4k_decode_workspace_bytes(int64_t nBlocks)
+static size_t ws_bytes(int64_t nBlocks, uint32_t markStride)
 {
-    if (nBlocks < 0) return 0;
     const size_t lst = (((size_t)nBlocks * 4 + 255) / 256) * 256;
-    return 256 + 3 * lst + (size_t)nBlocks * kMaxSeqFast * sizeof(uint32_t) + 256;
+    return 256 + 2 * lst + (size_t)nBlocks * markStride * sizeof(uint32_t) + 256;
+}
+
+size_t lz4k_decode_workspace_bytes(int64_t nBlocks)               /* any capacities (worst case: 32 KB of marks per block) */
+{
+    return nBlocks < 0 ? 0 : ws_bytes(nBlocks, (uint32_t)kMaxSeqFast);
+}
+
+size_t lz4k_decode_workspace_bytes_for(int64_t nBlocks, int perBlockCaps, int32_t dstCap)
+{
+    static const int32_t one = 1;                                 /* any non-NULL pointer: "capacities are per block" */
+    return nBlocks < 0 ? 0 : ws_bytes(nBlocks, mark_stride(perBlockCaps ? &one : nullptr, dstCap));
 }
 
 int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (a->nBlocks == 0) return 0;
-    static int impl = -1;                 /* developer A/B switch: LZ4K_EXPAND_IMPL=pieces selects the round-1 kernel */
-    if (impl < 0) { const char* v = getenv("LZ4K_EXPAND_IMPL"); impl = (v && v[0] == 'p') ? 1 : 0; }
-    {   /* opt in to the > 200 KB of dynamic shared memory (per device, cheap to repeat) */
-        cudaError_t e = cudaFuncSetAttribute(lz4_expand_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+    if (a->workspaceBytes < ws_bytes(a->nBlocks, mark_stride(a->dstCapArr, a->dstCap))) return (int)cudaErrorInvalidValue;
+    static int sms = 0, scanImpl = -1;
+    if (sms == 0) {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        /* opt in to the large dynamic shared memory (once; every device of a process runs the same kernels) */
+        cudaError_t e = cudaFuncSetAttribute(lz4_expand_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(lz4_scan_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanParSmem));
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(lz4_expand_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
-        if (e != cudaSuccess) return (int)e;
+        const char* env = getenv("LZ4K_SCAN_IMPL");               /* developer A/B switch: "thread" | "par" */
+        scanImpl = env ? (env[0] == 't' ? 0 : 1) : -1;
+        sms = v;
     }
     if (phases & 1) {
-        cudaError_t e = cudaMemsetAsync(a->workspace, 0, 256, s);     // WsHeader: list counters
+        cudaError_t e = cudaMemsetAsync(a->workspace, 0, 256, s);     // WsHeader: list counter
         if (e != cudaSuccess) return (int)e;
-#ifdef LZ4K_SCAN_V2
-        const int64_t grid = (a->nBlocks + 3) / 4;                    // 4 warps = 4 blocks per CTA
-        lz4_scan_v2_kernel<<<(unsigned)grid, 128, 0, s>>>(*a);
-#else
-        const int threads = 128;
-        const int64_t grid = (a->nBlocks + threads - 1) / threads;
-        lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
-#endif
+        /* one CTA per block pays off once a block holds a few hundred sequences; tiny blocks keep one thread each */
+        const bool par = scanImpl >= 0 ? scanImpl == 1 : (a->dstCapArr != nullptr || a->dstCap >= 8192);
+        if (par) {
+            const int64_t want = (int64_t)sms * 12;                   // 3 resident CTAs per SM, 4 rounds for balance
+            const int64_t grid = a->nBlocks < want ? a->nBlocks : want;
+            lz4_scan_par_kernel<<<(unsigned)grid, kScanLanes, sizeof(ScanParSmem), s>>>(*a);
+        } else {
+            const int threads = 128;
+            const int64_t grid = (a->nBlocks + threads - 1) / threads;
+            lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
+        }
         g_launches++;
     }
     if (phases & 2) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        WsView w = ws_view(a->workspace, a->nBlocks);
-        cudaError_t e = cudaMemsetAsync(&w.hdr->fastCursor, 0, sizeof(uint32_t), s);
-        if (e != cudaSuccess) return (int)e;
         int64_t grid = a->nBlocks < sms ? a->nBlocks : sms;          // persistent: one CTA per SM
-        if (impl == 1) lz4_expand_fast_kernel<<<(unsigned)grid, kFastThreads, sizeof(FastSmem), s>>>(*a);
-        else lz4_expand_rows_kernel<<<(unsigned)grid, kRowsThreads, sizeof(RowsSmem), s>>>(*a);
+        lz4_expand_rows_kernel<<<(unsigned)grid, kRowsThreads, sizeof(RowsSmem), s>>>(*a);
         g_launches++;
-        const int threads = 128;   // 4 warps = 4 blocks per CTA
-        const int64_t grid2 = (a->nBlocks * 32 + threads - 1) / threads;
+        const int threads = 128;                                     // 4 warps = 4 blocks per CTA, grid-stride over the slow list
+        int64_t grid2 = (a->nBlocks * 32 + threads - 1) / threads;
+        if (grid2 > (int64_t)sms * 16) grid2 = (int64_t)sms * 16;
         lz4_expand_generic_kernel<<<(unsigned)grid2, threads, 0, s>>>(*a);
         g_launches++;
     }

@@ -41,7 +41,9 @@ typedef struct {
     int64_t nBlocks;
 } lz4k_encode_args;
 
-size_t lz4k_decode_workspace_bytes(int64_t nBlocks);
+size_t lz4k_decode_workspace_bytes(int64_t nBlocks);   /* any capacities */
+/* tighter: per-block capacity array (perBlockCaps != 0) or one capacity for every block */
+size_t lz4k_decode_workspace_bytes_for(int64_t nBlocks, int perBlockCaps, int32_t dstCap);
 /* phases: bit 0 = scan (validate, sizes), bit 1 = expand (move bytes; needs a prior scan's outSize) */
 int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream);
 int lz4k_launch_encode(const lz4k_encode_args* a, void* stream);

@@ -38,19 +38,22 @@ constexpr int kLastLiterals = 5;
 constexpr int kMfLimit = 12;
 #endif
 
-SC_FN uint32_t ldb(const uint8_t* p) { return SC_LDG(p); }
-SC_FN void prefetch_l1(const uint8_t* p) { SC_PREFETCH_L1(p); }
-SC_FN uint32_t ld16(const uint8_t* p) { return SC_LDG(p) | (SC_LDG(p + 1) << 8); }
+/* G = true: the block lies in GLOBAL memory (read-only data cache loads, L1 prefetch hints);
+ * G = false: the block is staged in SHARED memory (plain loads through the generic address space). */
+template <bool G> SC_FN uint32_t ldb(const uint8_t* p) { return G ? (uint32_t)SC_LDG(p) : (uint32_t)*p; }
+template <bool G> SC_FN uint32_t ldw(const uint32_t* p) { return G ? SC_LDG(p) : *p; }
+template <bool G> SC_FN void prefetch_l1(const uint8_t* p) { if (G) SC_PREFETCH_L1(p); }
+template <bool G> SC_FN uint32_t ld16(const uint8_t* p) { return ldb<G>(p) | (ldb<G>(p + 1) << 8); }
 
 /* unaligned little-endian 32-bit read through two aligned words (never touches a word that holds
  * no requested byte) */
-SC_FN uint32_t ld32u(const uint8_t* p)
+template <bool G> SC_FN uint32_t ld32u(const uint8_t* p)
 {
     uintptr_t a = reinterpret_cast<uintptr_t>(p);
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
     uint32_t sh = (uint32_t)(a & 3) * 8;
-    uint32_t lo = SC_LDG(w);
-    uint32_t hi = sh ? SC_LDG(w + 1) : 0u;
+    uint32_t lo = ldw<G>(w);
+    uint32_t hi = sh ? ldw<G>(w + 1) : 0u;
     return SC_FUNNEL_R(lo, hi, sh);
 }
 
@@ -60,13 +63,13 @@ SC_FN uint32_t ld32u(const uint8_t* p)
 
 /* lz4.c:1978-2014.  ip advances exactly like the reference's pointer so that the error code
  * -(ip)-1 (lz4.c:2443) is reproduced. */
-SC_FN bool read_runlength(const uint8_t* src, int64_t& ip, int64_t ilimit, bool initialCheck, int64_t& total)
+template <bool G> SC_FN bool read_runlength(const uint8_t* src, int64_t& ip, int64_t ilimit, bool initialCheck, int64_t& total)
 {
     total = 0;
     if (initialCheck && ip >= ilimit) return false;
     uint32_t b;
     do {
-        b = ldb(src + ip);
+        b = ldb<G>(src + ip);
         ip++;
         total += b;
         if (ip > ilimit) return false;
@@ -78,9 +81,11 @@ SC_FN bool read_runlength(const uint8_t* src, int64_t& ip, int64_t ilimit, bool 
  * sequence of a block that may go to the shared-memory expand kernel.  With the marks the expand
  * kernel rebuilds all sequence records of a block in parallel (one lane per sequence) instead of
  * re-walking the token chain. */
-constexpr int kMaxSeqFast = 8192;              // record table of the fast expand kernel
+constexpr int kMaxSeqFast = 8192;              // most sequences a block of the shared-memory expand kernel may have
+/* `markCap` = number of mark slots the caller reserved for this block (<= kMaxSeqFast); a block that can be
+ * expanded from shared memory has at most capacity/4 + 1 sequences (every sequence but the last makes >= 4 bytes) */
 #define MARK_VISIT(tokpos, outpos)                                                              \
-    do { if (marks && nseq < (uint32_t)kMaxSeqFast) marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(outpos) << 16); } while (0)
+    do { if (marks && nseq < markCap) marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(outpos) << 16); } while (0)
 
 /* where the walk of one block stands between its two loops */
 struct ScanState {
@@ -98,36 +103,36 @@ struct ScanState {
  * error, absurd lengths) exits WITHOUT committing; the exact byte-wise code replays it.
  * Returns false for the one error it decides itself (offset before the start of the output,
  * lz4.c:2161), with st.ip at the reference's error position. */
-SC_FN bool scan_front(const uint8_t* __restrict__ src, int nIn, int capIn, ScanState& st, uint32_t* marks)
+template <bool G> SC_FN bool scan_front(const uint8_t* __restrict__ src, int nIn, int capIn, ScanState& st, uint32_t* marks, uint32_t markCap)
 {
     uint32_t nseq = st.nseq;
     int fip = 0, fop = 0, nextEvt = 0;
     const int nI = nIn, capI = capIn;
     while (fip <= nI - 26) {
         if (fip >= nextEvt) {                                      // L1 prefetch, once per 128 input bytes
-            if (fip + 128 < nI) prefetch_l1(src + fip + 128);
+            if (fip + 128 < nI) prefetch_l1<G>(src + fip + 128);
             nextEvt = ((fip >> 7) + 1) << 7;
         }
         MARK_VISIT(fip, fop);
-        const uint32_t v = ld32u(src + fip);                       // token, then up to 3 bytes that follow it
+        const uint32_t v = ld32u<G>(src + fip);                       // token, then up to 3 bytes that follow it
         const int mcode = (int)(v & 15u);
         int lit = (int)((v >> 4) & 15u), q = 1;
         if (lit == 15) {                                           // read_variable_length (lz4.c:2093), limit n-15
             uint32_t b = (v >> 8) & 0xFFu;
             lit += (int)b; q = 2;
-            while (b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { b = ldb(src + fip + q); q++; lit += (int)b; }
+            while (b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { b = ldb<G>(src + fip + q); q++; lit += (int)b; }
             if (b == 255u || fip + q > nI - 15) break;             // read limit / absurd run: replay byte-wise
             if ((uint32_t)fop + (uint32_t)lit > (uint32_t)(capI - 32) ||                 // lz4.c:2104 -> safe_literal_copy
                 (uint32_t)(fip + q) + (uint32_t)lit + 32u > (uint32_t)nI) break;         // (unsigned: sums may pass 2^31)
         }
         const int offPos = fip + q + lit;
-        const uint32_t v3 = ld32u(src + offPos);                   // offset (LE16), then the first match-length byte
+        const uint32_t v3 = ld32u<G>(src + offPos);                   // offset (LE16), then the first match-length byte
         const int off16 = (int)(v3 & 0xFFFFu);
         int mlen = mcode + kMinMatch, ipn = offPos + 2;
         if (mcode == 15) {                                         // read_variable_length (lz4.c:2128), limit n-4
             uint32_t b = (v3 >> 16) & 0xFFu;
             ipn++; mlen += (int)b;
-            while (b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { b = ldb(src + ipn); ipn++; mlen += (int)b; }
+            while (b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { b = ldb<G>(src + ipn); ipn++; mlen += (int)b; }
             if (b == 255u || ipn > nI - 4) break;
         }
         const int opn = fop + lit;
@@ -141,7 +146,7 @@ SC_FN bool scan_front(const uint8_t* __restrict__ src, int nIn, int capIn, ScanS
 }
 
 /* ---- the exact byte-wise walk (lz4.c:2083-2435) from the state `st` to the end of the block ---- */
-SC_FN int scan_tail(const uint8_t* __restrict__ src, int nIn, int capIn, const ScanState& st, uint32_t* nSeqOut, uint32_t* marks)
+template <bool G> SC_FN int scan_tail(const uint8_t* __restrict__ src, int nIn, int capIn, const ScanState& st, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap)
 {
     int64_t nextPrefetch = st.nextPrefetch;
     int64_t n = nIn, cap = capIn, ip = st.ip, op = st.op, ll = 0, ml = 0, add = 0;
@@ -151,25 +156,25 @@ SC_FN int scan_tail(const uint8_t* __restrict__ src, int nIn, int capIn, const S
     for (;;) {
         MARK_VISIT(ip, op);
         if (ip + 128 >= nextPrefetch) {                               // keep the input one 128-byte line ahead in L1
-            if (ip + 128 < n) prefetch_l1(src + ip + 128);
+            if (ip + 128 < n) prefetch_l1<G>(src + ip + 128);
             nextPrefetch = ip + 256;
         }
-        token = ldb(src + ip); ip++;
+        token = ldb<G>(src + ip); ip++;
         ll = token >> 4;
         ml = token & 15;
 
         if (fast) {                                                    // lz4.c:2083-2209
             if (ll == 15) {
-                if (!read_runlength(src, ip, n - 15, true, add)) goto bad;
+                if (!read_runlength<G>(src, ip, n - 15, true, add)) goto bad;
                 ll += add;
                 if (op + ll > cap - 32 || ip + ll > n - 32) { fast = false; goto safe_literals; }
             } else if (ip > n - 17) {
                 fast = false; goto safe_literals;
             }
             ip += ll; op += ll;
-            offset = ld16(src + ip); ip += 2;
+            offset = ld16<G>(src + ip); ip += 2;
             if (ml == 15) {
-                if (!read_runlength(src, ip, n - 4, false, add)) goto bad;
+                if (!read_runlength<G>(src, ip, n - 4, false, add)) goto bad;
                 ml += add;
             }
             ml += kMinMatch;
@@ -182,12 +187,12 @@ SC_FN int scan_tail(const uint8_t* __restrict__ src, int nIn, int capIn, const S
         /* safe loop, lz4.c:2215-2435 */
         if (ll != 15 && ip < n - 16 && op <= cap - 32) {               // two-stage shortcut :2230-2261
             op += ll; ip += ll;
-            offset = ld16(src + ip); ip += 2;
+            offset = ld16<G>(src + ip); ip += 2;
             if (ml != 15 && offset >= 8 && (int64_t)offset <= op) { op += ml + kMinMatch; nseq++; continue; }
             goto match_length;
         }
         if (ll == 15) {
-            if (!read_runlength(src, ip, n - 15, true, add)) goto bad;
+            if (!read_runlength<G>(src, ip, n - 15, true, add)) goto bad;
             ll += add;
         }
 safe_literals:
@@ -198,10 +203,10 @@ safe_literals:
             return (int)op;                                            // lz4.c:2439
         }
         ip += ll; op += ll;
-        offset = ld16(src + ip); ip += 2;
+        offset = ld16<G>(src + ip); ip += 2;
 match_length:
         if (ml == 15) {
-            if (!read_runlength(src, ip, n - 4, false, add)) goto bad;
+            if (!read_runlength<G>(src, ip, n - 4, false, add)) goto bad;
             ml += add;
         }
         ml += kMinMatch;
@@ -215,21 +220,21 @@ bad:
     return (int)(-ip) - 1;                                             // lz4.c:2443
 }
 
-SC_DEV int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut, uint32_t* marks)
+template <bool G> SC_DEV int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap)
 {
     ScanState st;
     st.ip = 0; st.op = 0; st.nextPrefetch = 128; st.nseq = 0;
 
     if (capIn < 0) return -1;                                          // lz4.c:2036
-    if (capIn == 0) return (nIn == 1 && ldb(src) == 0) ? 0 : -1;       // lz4.c:2064-2068
+    if (capIn == 0) return (nIn == 1 && ldb<G>(src) == 0) ? 0 : -1;       // lz4.c:2064-2068
     if (nIn <= 0) return -1;                                           // lz4.c:2069
     st.fast = (capIn >= 64);                                           // lz4.c:2076
 
-    if (st.fast && !scan_front(src, nIn, capIn, st, marks)) {
+    if (st.fast && !scan_front<G>(src, nIn, capIn, st, marks, markCap)) {
         *nSeqOut = 0;
         return (int)(-st.ip) - 1;                                      // lz4.c:2443
     }
-    return scan_tail(src, nIn, capIn, st, nSeqOut, marks);
+    return scan_tail<G>(src, nIn, capIn, st, nSeqOut, marks, markCap);
 }
 
 #endif /* LZ4_SCAN_CORE_H */

@@ -59,6 +59,9 @@ double oracle_time_compress(oracle_comp_fn fn, const uint8_t* src, int64_t srcSt
                             int64_t lastSize, uint8_t* dst, int64_t dstStride, int32_t dstCap, int accel,
                             int32_t* outSizes, int64_t nBlocks, int threads);
 /* multi-threaded datagen: segment k of segBytes gets seed seed0+k */
+void oracle_first_touch(uint8_t* dst, int64_t dstStride, int64_t nBlocks, int threads);
+void oracle_pack(const uint8_t* slots, int64_t slotStride, const int32_t* sizes, const int64_t* packOff,
+                 uint8_t* packed, int64_t nBlocks, int threads);
 void oracle_datagen_mt(uint8_t* buffer, size_t size, size_t segBytes, double matchProba, unsigned seed0, int threads);
 
 #ifdef __cplusplus

@@ -91,6 +91,10 @@ class Oracle(_Codec):
         lib.oracle_time_compress.restype = C.c_double
         lib.oracle_time_compress.argtypes = [C.c_void_p, _u8p, C.c_int64, C.c_int32, C.c_int64, _u8p, C.c_int64,
                                              C.c_int32, C.c_int, C.c_void_p, C.c_int64, C.c_int]
+        lib.oracle_first_touch.restype = None
+        lib.oracle_first_touch.argtypes = [_u8p, C.c_int64, C.c_int64, C.c_int]
+        lib.oracle_pack.restype = None
+        lib.oracle_pack.argtypes = [_u8p, C.c_int64, C.c_void_p, C.c_void_p, _u8p, C.c_int64, C.c_int]
         self._bound = lib.oracle_lz4_compress_bound
         self._compress = lib.oracle_lz4_compress_fast
         self._decompress = lib.oracle_lz4_decompress_safe
@@ -130,6 +134,14 @@ class Oracle(_Codec):
         t = self.lib.oracle_time_decompress(fn, _ptr(comp), offsets.ctypes.data, sizes.ctypes.data, _ptr(out),
                                             int(block_size), int(block_size), rets.ctypes.data, n, int(threads))
         return t, rets
+
+    def first_touch(self, buf, stride, n, threads):
+        """zero-fill buf (n x stride bytes) with the worker partition / CPU pinning of the timed passes"""
+        self.lib.oracle_first_touch(_ptr(buf), int(stride), int(n), int(threads))
+
+    def pack(self, slots, stride, sizes, offsets, packed, threads):
+        self.lib.oracle_pack(_ptr(slots), int(stride), sizes.ctypes.data, offsets.ctypes.data, _ptr(packed),
+                             len(sizes), int(threads))
 
     def time_compress(self, codec, src, block_size, out, out_stride, accel, threads):
         n = (len(src) + block_size - 1) // block_size

@@ -10,6 +10,6 @@
 extern "C" int scan_host(const uint8_t* src, int n, int cap, uint32_t* nSeqOut, uint32_t* marks)
 {
     *nSeqOut = 0;
-    return scan_block(src, n, cap, nSeqOut, marks);
+    return scan_block<true>(src, n, cap, nSeqOut, marks, (uint32_t)kMaxSeqFast);
 }
 extern "C" int scan_host_max_seq(void) { return kMaxSeqFast; }

@@ -1,43 +1,54 @@
-// CPU emulator of the warp-per-block scan (lz4_b200/csrc/lz4_scan_v2.h): TEST INFRASTRUCTURE.
-// Runs the 32 lanes of a warp phase by phase (the device puts a __syncwarp between phases) on the
+// CPU emulator of the intra-block parallel scan (lz4_b200/csrc/lz4_scan_par.h): TEST INFRASTRUCTURE.
+// Runs the NL lanes of a CTA phase by phase (the device puts a CTA barrier between phases) on the
 // host build of the same header and returns what the kernel would store for the block.
 #include <stdint.h>
 #include <string.h>
-#include "../../lz4_b200/csrc/lz4_scan_v2.h"
+#include "../../lz4_b200/csrc/lz4_scan_par.h"
+
+static int g_lanes = 128;
+extern "C" void scan_par_set_lanes(int nl) { g_lanes = nl; }
 
 // stats[0] = fix-up rounds, stats[1] = lane walks in the fix-up rounds, stats[2] = lane that finished the block
-extern "C" int scan_v2_host(const uint8_t* src, int n, int cap, uint32_t* nSeqOut, uint32_t* marks, int* stats)
+extern "C" int scan_par_host(const uint8_t* src, int n, int cap, uint32_t* nSeqOut, uint32_t* marks, int* stats)
 {
+    const int nl = g_lanes;
+    const uint32_t markCap = (uint32_t)kMaxSeqFast;
     *nSeqOut = 0;
     stats[0] = stats[1] = 0; stats[2] = -1;
-    if (cap < 64 || n < kSv2MinBytes) return scan_block(src, n, cap, nSeqOut, marks);   // lane 0, one-thread scan
-    SV2Shared S;
-    SV2Lane L[32];
+    if (cap < 64 || n < kSpMinBytes) return scan_block<true>(src, n, cap, nSeqOut, marks, markCap);   // lane 0, one-thread scan
+    static SpShared S;
+    static SpLane L[kSpMaxLanes];
     memset(&S, 0, sizeof(S));
-    for (int l = 0; l < 32; l++) sv2_phase0(l, L[l], S, src, n, cap);
+    for (int l = 0; l < nl; l++) sp_phase0<true>(l, nl, L[l], S, src, n, cap);
     for (;;) {
-        for (int l = 0; l < 32; l++) sv2_decide(l, L[l], S);
+        for (int l = 0; l < nl; l++) sp_decide(l, L[l], S);
         S.changed = 0;
-        for (int l = 0; l < 32; l++) { if (L[l].need && !L[l].newVoid) stats[1]++; sv2_redo(l, L[l], S, src, n, cap); }
+        for (int l = 0; l < nl; l++) { if (L[l].need && !L[l].newVoid) stats[1]++; sp_redo<true>(l, L[l], S, src, n, cap); }
         if (!S.changed) break;
         stats[0]++;
-        if (stats[0] > 64) return -1000000;                    // must converge within 32 rounds
+        if (stats[0] > 2 * nl) return -1000000;                // must converge within nl rounds
     }
-    for (int l = 0; l < 32; l++) sv2_write(l, L[l], S, src, n, cap, marks);
+    uint32_t cb = 0, ob = 0;
+    int first = nl - 1;
+    for (int l = 0; l < nl; l++) {
+        sp_write<true>(l, L[l], S, src, n, cap, cb, ob, marks, markCap);
+        cb += S.res[l].count; ob += S.res[l].olen;
+    }
+    for (int l = nl - 1; l >= 0; l--) if (S.end[l].kind != SP_RAN) first = l;
     S.ret = -2000000;
-    for (int l = 0; l < 32; l++) sv2_finish(l, S, src, n, cap, marks);
-    for (int l = 0; l < 32; l++) if (S.end[l].kind != SV2_RAN) { stats[2] = l; break; }
+    for (int l = 0; l < nl; l++) sp_finish<true>(l, first, S, src, n, cap, marks, markCap);
+    stats[2] = first;
     *nSeqOut = S.nseq;
     return S.ret;
 }
 
 // In-process differential fuzz: mutate a (valid) compressed block `iters` times, pick a capacity, and
-// compare the warp-per-block scan with the one-thread scan (return value, sequence count, marks).
+// compare the parallel scan with the one-thread scan (return value, sequence count, marks).
 // Returns the number of cases run, or -(1 + index) of the first mismatching case.
 namespace {
 struct FuzzRng { uint64_t s; uint32_t next() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 33); } };
 }
-extern "C" long long scan_v2_fuzz(const uint8_t* base, int n, int rawSize, int iters, uint64_t seed, long long* nErrors)
+extern "C" long long scan_par_fuzz(const uint8_t* base, int n, int rawSize, int iters, uint64_t seed, long long* nErrors)
 {
     FuzzRng r{seed * 0x9E3779B97F4A7C15ull + 1};
     uint8_t* buf = new uint8_t[(size_t)n + 64];
@@ -66,8 +77,8 @@ extern "C" long long scan_v2_fuzz(const uint8_t* base, int n, int rawSize, int i
         uint32_t ns1 = 0, ns2 = 0;
         int st[3];
         for (int i = 0; i < kMaxSeqFast; i++) { m1[i] = 0xABABABABu; m2[i] = 0xABABABABu; }
-        const int r1 = scan_block(p, (int)len, cap, &ns1, wm ? m1 : nullptr);
-        const int r2 = scan_v2_host(p, (int)len, cap, &ns2, wm ? m2 : nullptr, st);
+        const int r1 = scan_block<true>(p, (int)len, cap, &ns1, wm ? m1 : nullptr, (uint32_t)kMaxSeqFast);
+        const int r2 = scan_par_host(p, (int)len, cap, &ns2, wm ? m2 : nullptr, st);
         const uint32_t k = ns1 < (uint32_t)kMaxSeqFast ? ns1 : (uint32_t)kMaxSeqFast;
         if (r1 != r2 || (r1 > 0 && ns1 != ns2) || (r1 > 0 && wm && memcmp(m1, m2, sizeof(uint32_t) * k) != 0)) bad = -(1 + (long long)it);
         cases++;
