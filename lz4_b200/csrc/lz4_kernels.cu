@@ -134,9 +134,14 @@ __device__ __forceinline__ bool rows_eligible(int n, int cap, uint32_t nseq, uin
     return n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && nseq <= (uint32_t)kMaxSeqFast && nseq <= markStride;
 }
 
-/* ---- scan, one THREAD per block: batches of small blocks (a 4 KB block has ~150 sequences) ---- */
+/* ---- scan, one THREAD per block ----
+ * RING = true (default): every thread owns a kRingBytes ring in shared memory that cp.async keeps a few quarters
+ * ahead of its walk (lz4_scan_core.h: MemRing), so the token chain's dependent reads are shared-memory reads;
+ * RING = false: the round-1 kernel, reads through the read-only data cache with L1 prefetch hints. */
+template <bool RING>
 __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
 {
+    extern __shared__ __align__(16) uint8_t ringMem[];
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.nBlocks) return;
     const WsView w = ws_view(a);
@@ -145,7 +150,17 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
     int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
     uint32_t ns = 0;
     const bool wantMarks = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && w.markStride > 0);
-    int r = scan_block<true>(src, n, cap, &ns, wantMarks ? (w.marks + b * w.markStride) : nullptr, w.markStride);
+    uint32_t* marks = wantMarks ? (w.marks + b * w.markStride) : nullptr;
+    int r;
+    if (RING && n > 0) {
+        MemRing mem;
+        mem.init(src, n, ringMem + (size_t)threadIdx.x * kRingStride);
+        r = scan_block(mem, n, cap, &ns, marks, w.markStride);
+        mem.cp.wait(0);                                        /* no copy of this thread is in flight when it exits */
+    } else {
+        MemPtr<true> mem{src};
+        r = scan_block(mem, n, cap, &ns, marks, w.markStride);
+    }
     a.outSize[b] = r;
     w.nSeq[b] = ns;
     if (r > 0 && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
@@ -169,27 +184,27 @@ struct ScanParSmem {
     alignas(8) uint64_t mbar;
 };
 
-template <bool G>
-__device__ __forceinline__ void scan_par_block(ScanParSmem& S, const uint8_t* src, int n, int cap, uint32_t* marks, uint32_t markCap,
+template <class M>
+__device__ __forceinline__ void scan_par_block(ScanParSmem& S, M& mem, int n, int cap, uint32_t* marks, uint32_t markCap,
                                                int& ret, uint32_t& nseq)
 {
     const int lane = threadIdx.x, nl = kScanLanes;
     if (cap < 64 || n < kSpMinBytes) {
-        if (lane == 0) { uint32_t ns = 0; S.sp.ret = scan_block<G>(src, n, cap, &ns, marks, markCap); S.sp.nseq = ns; }
+        if (lane == 0) { uint32_t ns = 0; S.sp.ret = scan_block(mem, n, cap, &ns, marks, markCap); S.sp.nseq = ns; }
         __syncthreads();
         ret = S.sp.ret; nseq = S.sp.nseq;
         __syncthreads();
         return;
     }
     SpLane L;
-    sp_phase0<G>(lane, nl, L, S.sp, src, n, cap);
+    sp_phase0(lane, nl, L, S.sp, mem, n, cap);
     __syncthreads();
     for (;;) {
         sp_decide(lane, L, S.sp);
         __syncthreads();                                   /* everybody has read S.changed's previous value and its neighbour's result */
         if (lane == 0) S.sp.changed = 0;
         __syncthreads();
-        sp_redo<G>(lane, L, S.sp, src, n, cap);
+        sp_redo(lane, L, S.sp, mem, n, cap);
         __syncthreads();
         if (!S.sp.changed) break;
     }
@@ -205,10 +220,10 @@ __device__ __forceinline__ void scan_par_block(ScanParSmem& S, const uint8_t* sr
     __syncthreads();
     uint32_t cb = ci - c, ob = oi - o;
     for (int wq = 0; wq < (lane >> 5); wq++) { cb += S.warpCnt[wq]; ob += S.warpLen[wq]; }
-    sp_write<G>(lane, L, S.sp, src, n, cap, cb, ob, marks, markCap);
+    sp_write(lane, L, S.sp, mem, n, cap, cb, ob, marks, markCap);
     if (S.sp.end[lane].kind != SP_RAN) atomicMin(&S.first, lane);
     __syncthreads();
-    sp_finish<G>(lane, S.first, S.sp, src, n, cap, marks, markCap);
+    sp_finish(lane, S.first, S.sp, mem, n, cap, marks, markCap);
     __syncthreads();
     ret = S.sp.ret; nseq = S.sp.nseq;
     __syncthreads();
@@ -241,11 +256,13 @@ __global__ void __launch_bounds__(kScanLanes) lz4_scan_par_kernel(lz4k_decode_ar
             }
             while (!mbar_try_wait(&S.mbar, parity)) { }
             parity ^= 1;
-            scan_par_block<false>(S, S.in + head, n, cap, marks, w.markStride, r, ns);
+            MemPtr<false> mem{S.in + head};
+            scan_par_block(S, mem, n, cap, marks, w.markStride, r, ns);
         } else if (n > 65535 && cap >= 64) {
-            scan_par_block<true>(S, src, n, cap, marks, w.markStride, r, ns);
+            MemPtr<true> mem{src};
+            scan_par_block(S, mem, n, cap, marks, w.markStride, r, ns);
         } else {                                               /* degenerate arguments: the one-thread code decides (lz4.c:2036, :2064-2069) */
-            if (tid == 0) { uint32_t q = 0; S.sp.ret = scan_block<true>(src, n, cap, &q, nullptr, 0u); S.sp.nseq = q; }
+            if (tid == 0) { uint32_t q = 0; MemPtr<true> mem{src}; S.sp.ret = scan_block(mem, n, cap, &q, nullptr, 0u); S.sp.nseq = q; }
             __syncthreads();
             r = S.sp.ret; ns = S.sp.nseq;
             __syncthreads();
@@ -401,17 +418,19 @@ __device__ __forceinline__ void rows_resolve(uint32_t (&sa)[LZ4K_ROWS_RPT], cons
     uint32_t hi = sa[0];
     #pragma unroll
     for (int r = 1; r < LZ4K_ROWS_RPT; r++) hi = max(hi, sa[r]);
-    if (hi >= waveS) {                                         /* sources inside this wave: follow them */
+    while (hi >= waveS) {                                      /* sources inside this wave: follow them, all rows of the thread at once */
+        hi = 0;
         #pragma unroll
         for (int r = 0; r < LZ4K_ROWS_RPT; r++) {
             uint32_t x = sa[r];
-            while (x >= waveS) {
+            if (x >= waveS) {
                 const uint32_t q = x - outS;
                 const uint2 row = lds_u64(rowsS + ((q >> 5) << 3));
                 const uint32_t j = row.y + (uint32_t)__popc(row.x & (0xFFFFFFFFu >> (31u - (q & 31u))));
                 x += lds_u32(tabS + (j << 2));
+                sa[r] = x;
             }
-            sa[r] = x;
+            hi = max(hi, x);
         }
     }
 }
@@ -432,19 +451,25 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
     uint32_t parity = 0, wpar = 0;
 
     /* a block's arguments; n = 0 marks "nothing to do here" (past the end, rejected by the scan, or a block of the
-     * generic kernel: input > 65535 bytes, capacity > 64 KB, more than kMaxSeqFast sequences) */
-    auto fetch = [&](int64_t b) {
-        RowsDesc d;
-        d.b = b; d.src = nullptr; d.dst = nullptr; d.n = 0; d.total = 0; d.nseq = 0;
+     * generic kernel: input > 65535 bytes, capacity > 64 KB, more than kMaxSeqFast sequences).  The raw loads are
+     * issued a block ahead (fetchRaw) and only looked at after the waves (finish), so nobody waits for them. */
+    struct Raw { int64_t b, off, dOff; int n, total, cap; uint32_t ns; };
+    auto fetchRaw = [&](int64_t b) {
+        Raw r;
+        r.b = b; r.off = 0; r.dOff = 0; r.n = 0; r.total = 0; r.cap = 0; r.ns = 0;
         if (b < a.nBlocks) {
-            const int n = a.srcSize[b], total = a.outSize[b];
-            const int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
-            const uint32_t ns = w.nSeq[b];
-            if (total > 0 && rows_eligible(n, cap, ns, w.markStride)) {
-                d.src = a.src + a.srcOff[b];
-                d.dst = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
-                d.n = n; d.total = total; d.nseq = (int)ns;
-            }
+            r.n = a.srcSize[b]; r.total = a.outSize[b]; r.ns = w.nSeq[b]; r.off = a.srcOff[b];
+            r.cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
+            r.dOff = a.dstOff ? a.dstOff[b] : b * a.dstStride;
+        }
+        return r;
+    };
+    auto finish = [&](const Raw& r) {
+        RowsDesc d;
+        d.b = r.b; d.src = nullptr; d.dst = nullptr; d.n = 0; d.total = 0; d.nseq = 0;
+        if (r.b < a.nBlocks && r.total > 0 && rows_eligible(r.n, r.cap, r.ns, w.markStride)) {
+            d.src = a.src + r.off; d.dst = a.dst + r.dOff;
+            d.n = r.n; d.total = r.total; d.nseq = (int)r.ns;
         }
         return d;
     };
@@ -459,7 +484,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
     if (tid == 0) { mbar_init(&S.mbar, 1); mbar_init(&S.wbar, kRowsThreads / 32); }
     if (tid < 4) reinterpret_cast<uint32_t*>(S.zero)[tid] = 0;
     if (tid == 0) {
-        S.desc[0] = fetch(blockIdx.x);
+        S.desc[0] = finish(fetchRaw(blockIdx.x));
         if (S.desc[0].n > 0) issueLoad(S.desc[0]);
     }
     __syncthreads();
@@ -472,11 +497,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
         const int64_t b = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
         if (b >= a.nBlocks) break;
         const RowsDesc d = S.desc[it & 1];
-        RowsDesc dn;                                           /* the next block's arguments: loads issued now, used after the waves */
-        if (tid == 0) dn = fetch(b + gridDim.x);
+        Raw rawNext;                                           /* the next block's arguments: loads issued now, used after the waves */
+        if (tid == 0) rawNext = fetchRaw(b + gridDim.x);
         if (d.n == 0) {                                        /* not a block of this kernel */
             __syncthreads();
-            if (tid == 0) { S.desc[(it + 1) & 1] = dn; if (dn.n > 0) issueLoad(dn); }
+            if (tid == 0) { const RowsDesc dn = finish(rawNext); S.desc[(it + 1) & 1] = dn; if (dn.n > 0) issueLoad(dn); }
             __syncthreads();
             continue;
         }
@@ -604,6 +629,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
 
         /* `in`, `tab` and `rows` are dead: start the next block's load before anything else */
         if (tid == 0) {
+            const RowsDesc dn = finish(rawNext);
             S.desc[(it + 1) & 1] = dn;
             if (dn.n > 0) issueLoad(dn);
         }
@@ -969,15 +995,16 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         cudaError_t e = cudaFuncSetAttribute(lz4_expand_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(lz4_scan_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanParSmem));
         if (e != cudaSuccess) return (int)e;
-        const char* env = getenv("LZ4K_SCAN_IMPL");               /* developer A/B switch: "thread" | "par" */
-        scanImpl = env ? (env[0] == 't' ? 0 : 1) : -1;
+        const char* env = getenv("LZ4K_SCAN_IMPL");               /* developer A/B switch: "thread" (no ring) | "ring" | "par" */
+        scanImpl = env ? (env[0] == 't' ? 0 : env[0] == 'p' ? 1 : 2) : -1;
         sms = v;
     }
     if (phases & 1) {
         cudaError_t e = cudaMemsetAsync(a->workspace, 0, 256, s);     // WsHeader: list counter
         if (e != cudaSuccess) return (int)e;
-        /* one CTA per block pays off once a block holds a few hundred sequences; tiny blocks keep one thread each */
-        const bool par = scanImpl >= 0 ? scanImpl == 1 : (a->dstCapArr != nullptr || a->dstCap >= 8192);
+        /* measured (profiles/): the lanes of the parallel scan re-walk their segments several times, ~10x the instructions of the
+         * one-thread scan, so it only pays for blocks far beyond 64 KB (lz4frame's 4 MB blocks: 150 000 dependent steps for one thread) */
+        const bool par = (scanImpl == 0 || scanImpl == 2) ? false : scanImpl == 1 ? true : (a->dstCapArr == nullptr && a->dstCap > 65536);
         if (par) {
             const int64_t want = (int64_t)sms * 12;                   // 3 resident CTAs per SM, 4 rounds for balance
             const int64_t grid = a->nBlocks < want ? a->nBlocks : want;
@@ -985,7 +1012,8 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         } else {
             const int threads = 128;
             const int64_t grid = (a->nBlocks + threads - 1) / threads;
-            lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
+            if (scanImpl == 0) lz4_scan_kernel<false><<<(unsigned)grid, threads, 0, s>>>(*a);
+            else lz4_scan_kernel<true><<<(unsigned)grid, threads, threads * kRingStride, s>>>(*a);
         }
         g_launches++;
     }

@@ -15,12 +15,14 @@
 
 #if defined(__CUDACC__)
 #define SC_FN __device__ __forceinline__
+#define SC_MFN __device__ __forceinline__     /* member functions */
 #define SC_DEV __device__
 #define SC_LDG(p) __ldg(p)
 #define SC_FUNNEL_R(lo, hi, s) __funnelshift_r((lo), (hi), (s))
 #define SC_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #else
 #define SC_FN static inline
+#define SC_MFN inline
 #define SC_DEV static inline
 #define SC_LDG(p) (*(p))
 static inline uint32_t sc_funnel_r_host(uint32_t lo, uint32_t hi, uint32_t s)
@@ -38,11 +40,21 @@ constexpr int kLastLiterals = 5;
 constexpr int kMfLimit = 12;
 #endif
 
-/* G = true: the block lies in GLOBAL memory (read-only data cache loads, L1 prefetch hints);
- * G = false: the block is staged in SHARED memory (plain loads through the generic address space). */
+/* ---------------------------------------------------------------------------------------------
+ * How the scan reads the compressed block.  Every read goes through a "memory" object:
+ *   MemPtr<true>   the block lies in GLOBAL memory (read-only data cache loads, L1 prefetch hints)
+ *   MemPtr<false>  the block is staged in SHARED memory (plain loads through the generic address space)
+ *   MemRing        the block lies in global memory and a per-thread RING in shared memory runs ahead of
+ *                  the walk (cp.async, 64-byte quarters): the dependent reads of the token chain then cost a
+ *                  shared-memory access instead of an L2 / HBM round trip (one thread per block, 32 unrelated
+ *                  streams per warp: without the ring nearly every warp-level load waits for a cache miss)
+ * b(i) / u16(i) / u32(i) read bytes [i, i+1/2/4) of the block; ensure(i) must have been called with a
+ * position <= i such that i + 4 <= position + kMemAhead since the last jump.
+ * ------------------------------------------------------------------------------------------- */
+constexpr int kMemAhead = 32;              /* bytes that ensure(i) makes readable: [i, i + kMemAhead) */
+
 template <bool G> SC_FN uint32_t ldb(const uint8_t* p) { return G ? (uint32_t)SC_LDG(p) : (uint32_t)*p; }
 template <bool G> SC_FN uint32_t ldw(const uint32_t* p) { return G ? SC_LDG(p) : *p; }
-template <bool G> SC_FN void prefetch_l1(const uint8_t* p) { if (G) SC_PREFETCH_L1(p); }
 template <bool G> SC_FN uint32_t ld16(const uint8_t* p) { return ldb<G>(p) | (ldb<G>(p + 1) << 8); }
 
 /* unaligned little-endian 32-bit read through two aligned words (never touches a word that holds
@@ -57,19 +69,147 @@ template <bool G> SC_FN uint32_t ld32u(const uint8_t* p)
     return SC_FUNNEL_R(lo, hi, sh);
 }
 
+template <bool G> struct MemPtr {
+    const uint8_t* p;
+    SC_MFN uint32_t b(int64_t i) const { return ldb<G>(p + i); }
+    SC_MFN uint32_t u16(int64_t i) const { return ld16<G>(p + i); }
+    SC_MFN uint32_t u32(int64_t i) const { return ld32u<G>(p + i); }
+    SC_MFN void ensure(int64_t) const { }
+    SC_MFN void prefetch(int64_t i) const { if (G) SC_PREFETCH_L1(p + i); }
+    static constexpr bool kPrefetch = G;
+};
+
+#ifndef LZ4K_RING_BYTES
+#define LZ4K_RING_BYTES 256
+#endif
+constexpr int kRingBytes = LZ4K_RING_BYTES;           /* per-thread window, power of two, 4 quarters */
+constexpr int kRingQuarter = kRingBytes / 4;
+constexpr int kRingStride = kRingBytes + 16;         /* rings of neighbouring lanes start in different banks */
+static_assert((kRingBytes & (kRingBytes - 1)) == 0 && kRingQuarter % 16 == 0 && kRingQuarter >= 2 * kMemAhead, "ring geometry");
+
+/* the asynchronous copy engine of the ring: cp.async on the device; the host build (tests/emul) queues the copies and
+ * performs them at the wait, poisoning the destination in between, so that a read before the wait shows up in the tests */
+#if defined(__CUDACC__)
+struct RingCopier {
+    SC_MFN void copy16(uint8_t* dst, const uint8_t* src) const
+    {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    }
+    SC_MFN void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    SC_MFN void wait(int pendingAllowed) const            /* groups complete in order: allow the newest `pendingAllowed` to stay in flight */
+    {
+        if (pendingAllowed >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (pendingAllowed == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+};
+#else
+struct RingCopier {
+    struct Job { uint8_t* dst; const uint8_t* src; int group; };
+    mutable Job jobs[64];
+    mutable int nJobs = 0, nextGroup = 0, doneGroups = 0;
+    void copy16(uint8_t* dst, const uint8_t* src) const
+    {
+        for (int k = 0; k < 16; k++) dst[k] = 0xA7;      /* poison until the wait */
+        jobs[nJobs++] = Job{dst, src, nextGroup};
+    }
+    void commit() const { nextGroup++; }
+    void wait(int pendingAllowed) const
+    {
+        const int upTo = nextGroup - pendingAllowed;     /* groups [0, upTo) must be complete */
+        int kept = 0;
+        for (int j = 0; j < nJobs; j++) {
+            if (jobs[j].group < upTo) { for (int k = 0; k < 16; k++) jobs[j].dst[k] = jobs[j].src[k]; }
+            else jobs[kept++] = jobs[j];
+        }
+        nJobs = kept;
+        if (upTo > doneGroups) doneGroups = upTo;
+    }
+};
+#endif
+
+struct MemRing {
+    const uint8_t* g16;        /* 16-byte aligned address at or below the block's first byte */
+    uint8_t* ring;             /* this thread's kRingBytes of shared memory (16-byte aligned) */
+    int head;                  /* block byte i lives at aligned-space position i + head */
+    int aEnd;                  /* head + n: first aligned-space position past the block */
+    int base;                  /* the ring covers aligned-space [base, base + kRingBytes); multiple of kRingQuarter */
+    int ready;                 /* everything in [base, ready) has arrived */
+    int sent;                  /* quarters in [ready, sent) are in flight, one cp.async group each */
+    RingCopier cp;
+
+    SC_MFN void init(const uint8_t* src, int n, uint8_t* ringMem)
+    {
+        head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+        g16 = src - head;
+        ring = ringMem;
+        aEnd = head + n;
+        base = ready = sent = 0;
+        top_up();
+    }
+    /* issue every quarter the ring has room for (16-byte granules that start inside the block only: at most 15 bytes
+     * past the block's end are read, the same padding rule as the bulk loads of the expand kernel) */
+    SC_MFN void top_up()
+    {
+        while (sent < base + kRingBytes && sent < aEnd) {
+            #pragma unroll
+            for (int k = 0; k < kRingQuarter; k += 16)
+                if (sent + k < aEnd) cp.copy16(ring + ((sent + k) & (kRingBytes - 1)), g16 + sent + k);
+            cp.commit();
+            sent += kRingQuarter;
+        }
+    }
+    SC_MFN void ensure(int64_t i)
+    {
+        const int a = (int)i + head;
+        const int q = a & ~(kRingQuarter - 1);
+        if (q != base) {
+            if (q > base && q < sent) {                       /* the walk moved on: free the quarters behind it */
+                base = q;
+                if (ready < base) ready = base;               /* (skipped quarters stay in flight; their groups are waited for in order) */
+            } else {                                          /* a jump out of the window (long literal run, or the byte-wise replay going back) */
+                cp.wait(0);
+                base = ready = sent = q;
+            }
+            top_up();
+        }
+        const int need = (a + kMemAhead < aEnd ? a + kMemAhead : aEnd);
+        if (need > ready) {
+            const int upto = (need + kRingQuarter - 1) & ~(kRingQuarter - 1);      /* quarters below `upto` must have arrived */
+            const int later = (sent - upto) / kRingQuarter;                         /* groups issued after them */
+            cp.wait(later > 0 ? later : 0);
+            ready = upto < sent ? upto : sent;
+        }
+    }
+    SC_MFN uint32_t b(int64_t i) const { return ring[((int)i + head) & (kRingBytes - 1)]; }
+    SC_MFN uint32_t u16(int64_t i) const { return b(i) | (b(i + 1) << 8); }
+    SC_MFN uint32_t u32(int64_t i) const
+    {
+        const int a = (int)i + head;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(ring);
+        const uint32_t sh = (uint32_t)(a & 3) * 8;
+        const uint32_t lo = w[(a & (kRingBytes - 1)) >> 2];
+        const uint32_t hi = sh ? w[((a + 4) & (kRingBytes - 1)) >> 2] : 0u;
+        return SC_FUNNEL_R(lo, hi, sh);
+    }
+    SC_MFN void prefetch(int64_t) const { }
+    static constexpr bool kPrefetch = false;
+};
+
 /* =============================================================================================
  * scan: exact acceptance + return value of LZ4_decompress_safe, one thread per block
  * ============================================================================================= */
 
 /* lz4.c:1978-2014.  ip advances exactly like the reference's pointer so that the error code
  * -(ip)-1 (lz4.c:2443) is reproduced. */
-template <bool G> SC_FN bool read_runlength(const uint8_t* src, int64_t& ip, int64_t ilimit, bool initialCheck, int64_t& total)
+template <class M> SC_FN bool read_runlength(M& mem, int64_t& ip, int64_t ilimit, bool initialCheck, int64_t& total)
 {
     total = 0;
     if (initialCheck && ip >= ilimit) return false;
     uint32_t b;
     do {
-        b = ldb<G>(src + ip);
+        mem.ensure(ip);
+        b = mem.b(ip);
         ip++;
         total += b;
         if (ip > ilimit) return false;
@@ -103,36 +243,38 @@ struct ScanState {
  * error, absurd lengths) exits WITHOUT committing; the exact byte-wise code replays it.
  * Returns false for the one error it decides itself (offset before the start of the output,
  * lz4.c:2161), with st.ip at the reference's error position. */
-template <bool G> SC_FN bool scan_front(const uint8_t* __restrict__ src, int nIn, int capIn, ScanState& st, uint32_t* marks, uint32_t markCap)
+template <class M> SC_FN bool scan_front(M& mem, int nIn, int capIn, ScanState& st, uint32_t* marks, uint32_t markCap)
 {
     uint32_t nseq = st.nseq;
     int fip = 0, fop = 0, nextEvt = 0;
     const int nI = nIn, capI = capIn;
     while (fip <= nI - 26) {
         if (fip >= nextEvt) {                                      // L1 prefetch, once per 128 input bytes
-            if (fip + 128 < nI) prefetch_l1<G>(src + fip + 128);
+            if (fip + 128 < nI) mem.prefetch(fip + 128);
             nextEvt = ((fip >> 7) + 1) << 7;
         }
         MARK_VISIT(fip, fop);
-        const uint32_t v = ld32u<G>(src + fip);                       // token, then up to 3 bytes that follow it
+        mem.ensure(fip);                                           // [fip, fip + kMemAhead) is readable: token, short literals, offset
+        const uint32_t v = mem.u32(fip);                       // token, then up to 3 bytes that follow it
         const int mcode = (int)(v & 15u);
         int lit = (int)((v >> 4) & 15u), q = 1;
         if (lit == 15) {                                           // read_variable_length (lz4.c:2093), limit n-15
             uint32_t b = (v >> 8) & 0xFFu;
             lit += (int)b; q = 2;
-            while (b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { b = ldb<G>(src + fip + q); q++; lit += (int)b; }
+            while (b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { mem.ensure(fip + q); b = mem.b(fip + q); q++; lit += (int)b; }
             if (b == 255u || fip + q > nI - 15) break;             // read limit / absurd run: replay byte-wise
             if ((uint32_t)fop + (uint32_t)lit > (uint32_t)(capI - 32) ||                 // lz4.c:2104 -> safe_literal_copy
                 (uint32_t)(fip + q) + (uint32_t)lit + 32u > (uint32_t)nI) break;         // (unsigned: sums may pass 2^31)
+            mem.ensure(fip + q + lit);                             // a long literal run: the offset lies beyond the window
         }
         const int offPos = fip + q + lit;
-        const uint32_t v3 = ld32u<G>(src + offPos);                   // offset (LE16), then the first match-length byte
+        const uint32_t v3 = mem.u32(offPos);                   // offset (LE16), then the first match-length byte
         const int off16 = (int)(v3 & 0xFFFFu);
         int mlen = mcode + kMinMatch, ipn = offPos + 2;
         if (mcode == 15) {                                         // read_variable_length (lz4.c:2128), limit n-4
             uint32_t b = (v3 >> 16) & 0xFFu;
             ipn++; mlen += (int)b;
-            while (b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { b = ldb<G>(src + ipn); ipn++; mlen += (int)b; }
+            while (b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { mem.ensure(ipn); b = mem.b(ipn); ipn++; mlen += (int)b; }
             if (b == 255u || ipn > nI - 4) break;
         }
         const int opn = fop + lit;
@@ -146,7 +288,7 @@ template <bool G> SC_FN bool scan_front(const uint8_t* __restrict__ src, int nIn
 }
 
 /* ---- the exact byte-wise walk (lz4.c:2083-2435) from the state `st` to the end of the block ---- */
-template <bool G> SC_FN int scan_tail(const uint8_t* __restrict__ src, int nIn, int capIn, const ScanState& st, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap)
+template <class M> SC_FN int scan_tail(M& mem, int nIn, int capIn, const ScanState& st, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap)
 {
     int64_t nextPrefetch = st.nextPrefetch;
     int64_t n = nIn, cap = capIn, ip = st.ip, op = st.op, ll = 0, ml = 0, add = 0;
@@ -156,25 +298,27 @@ template <bool G> SC_FN int scan_tail(const uint8_t* __restrict__ src, int nIn, 
     for (;;) {
         MARK_VISIT(ip, op);
         if (ip + 128 >= nextPrefetch) {                               // keep the input one 128-byte line ahead in L1
-            if (ip + 128 < n) prefetch_l1<G>(src + ip + 128);
+            if (ip + 128 < n) mem.prefetch(ip + 128);
             nextPrefetch = ip + 256;
         }
-        token = ldb<G>(src + ip); ip++;
+        mem.ensure(ip);
+        token = mem.b(ip); ip++;
         ll = token >> 4;
         ml = token & 15;
 
         if (fast) {                                                    // lz4.c:2083-2209
             if (ll == 15) {
-                if (!read_runlength<G>(src, ip, n - 15, true, add)) goto bad;
+                if (!read_runlength(mem, ip, n - 15, true, add)) goto bad;
                 ll += add;
                 if (op + ll > cap - 32 || ip + ll > n - 32) { fast = false; goto safe_literals; }
             } else if (ip > n - 17) {
                 fast = false; goto safe_literals;
             }
             ip += ll; op += ll;
-            offset = ld16<G>(src + ip); ip += 2;
+            mem.ensure(ip);
+            offset = mem.u16(ip); ip += 2;
             if (ml == 15) {
-                if (!read_runlength<G>(src, ip, n - 4, false, add)) goto bad;
+                if (!read_runlength(mem, ip, n - 4, false, add)) goto bad;
                 ml += add;
             }
             ml += kMinMatch;
@@ -187,12 +331,13 @@ template <bool G> SC_FN int scan_tail(const uint8_t* __restrict__ src, int nIn, 
         /* safe loop, lz4.c:2215-2435 */
         if (ll != 15 && ip < n - 16 && op <= cap - 32) {               // two-stage shortcut :2230-2261
             op += ll; ip += ll;
-            offset = ld16<G>(src + ip); ip += 2;
+            mem.ensure(ip);
+            offset = mem.u16(ip); ip += 2;
             if (ml != 15 && offset >= 8 && (int64_t)offset <= op) { op += ml + kMinMatch; nseq++; continue; }
             goto match_length;
         }
         if (ll == 15) {
-            if (!read_runlength<G>(src, ip, n - 15, true, add)) goto bad;
+            if (!read_runlength(mem, ip, n - 15, true, add)) goto bad;
             ll += add;
         }
 safe_literals:
@@ -203,10 +348,11 @@ safe_literals:
             return (int)op;                                            // lz4.c:2439
         }
         ip += ll; op += ll;
-        offset = ld16<G>(src + ip); ip += 2;
+        mem.ensure(ip);
+        offset = mem.u16(ip); ip += 2;
 match_length:
         if (ml == 15) {
-            if (!read_runlength<G>(src, ip, n - 4, false, add)) goto bad;
+            if (!read_runlength(mem, ip, n - 4, false, add)) goto bad;
             ml += add;
         }
         ml += kMinMatch;
@@ -220,21 +366,21 @@ bad:
     return (int)(-ip) - 1;                                             // lz4.c:2443
 }
 
-template <bool G> SC_DEV int scan_block(const uint8_t* __restrict__ src, int nIn, int capIn, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap)
+template <class M> SC_DEV int scan_block(M& mem, int nIn, int capIn, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap)
 {
     ScanState st;
     st.ip = 0; st.op = 0; st.nextPrefetch = 128; st.nseq = 0;
 
     if (capIn < 0) return -1;                                          // lz4.c:2036
-    if (capIn == 0) return (nIn == 1 && ldb<G>(src) == 0) ? 0 : -1;       // lz4.c:2064-2068
+    if (capIn == 0) { if (nIn != 1) return -1; mem.ensure(0); return mem.b(0) == 0 ? 0 : -1; }   // lz4.c:2064-2068
     if (nIn <= 0) return -1;                                           // lz4.c:2069
     st.fast = (capIn >= 64);                                           // lz4.c:2076
 
-    if (st.fast && !scan_front<G>(src, nIn, capIn, st, marks, markCap)) {
+    if (st.fast && !scan_front(mem, nIn, capIn, st, marks, markCap)) {
         *nSeqOut = 0;
         return (int)(-st.ip) - 1;                                      // lz4.c:2443
     }
-    return scan_tail<G>(src, nIn, capIn, st, nSeqOut, marks, markCap);
+    return scan_tail(mem, nIn, capIn, st, nSeqOut, marks, markCap);
 }
 
 #endif /* LZ4_SCAN_CORE_H */

@@ -65,38 +65,38 @@ struct SpLane {                            /* registers of one lane */
 
 /* One walk over [from, segEnd): scan_front's loop body with the output position relative (COUNT) or
  * absolute (WRITE).  Position-only rules apply in both passes, output-dependent rules in WRITE only. */
-template <bool G, bool WRITE>
-SC_FN void sp_walk(const uint8_t* __restrict__ src, int nI, int capI, int from, int segEnd,
+template <class M, bool WRITE>
+SC_FN void sp_walk(M& mem, int nI, int capI, int from, int segEnd,
                    uint32_t opBase, uint32_t seqBase, uint32_t* marks, uint32_t markCap, SpRes& R, SpEnd& E)
 {
     int fip = from, nextEvt = 0, stop = 0, kind = SP_RAN, errIp = 0;
     uint32_t fop = opBase, cnt = 0;
     while (fip < segEnd) {
         if (fip > nI - 26) { stop = 1; kind = SP_END; break; }
-        if (G && fip >= nextEvt) {                                 // L1 prefetch, once per 128 input bytes
-            if (fip + 128 < nI) prefetch_l1<G>(src + fip + 128);
+        if (M::kPrefetch && fip >= nextEvt) {                      // L1 prefetch, once per 128 input bytes
+            if (fip + 128 < nI) mem.prefetch(fip + 128);
             nextEvt = ((fip >> 7) + 1) << 7;
         }
         if (WRITE) { const uint32_t nseq = seqBase + cnt; MARK_VISIT(fip, fop); }
-        const uint32_t v = ld32u<G>(src + fip);
+        const uint32_t v = mem.u32(fip);
         const int mcode = (int)(v & 15u);
         int lit = (int)((v >> 4) & 15u), q = 1;
         if (lit == 15) {
             uint32_t b = (v >> 8) & 0xFFu;
             lit += (int)b; q = 2;
-            while (b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { b = ldb<G>(src + fip + q); q++; lit += (int)b; }
+            while (b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { b = mem.b(fip + q); q++; lit += (int)b; }
             if (b == 255u || fip + q > nI - 15) { stop = 1; kind = SP_END; break; }
             if ((uint32_t)(fip + q) + (uint32_t)lit + 32u > (uint32_t)nI) { stop = 1; kind = SP_END; break; }
             if (WRITE && fop + (uint32_t)lit > (uint32_t)(capI - 32)) { kind = SP_END; break; }
         }
         const int offPos = fip + q + lit;
-        const uint32_t v3 = ld32u<G>(src + offPos);
+        const uint32_t v3 = mem.u32(offPos);
         const uint32_t off16 = v3 & 0xFFFFu;
         int mlen = mcode + kMinMatch, ipn = offPos + 2;
         if (mcode == 15) {
             uint32_t b = (v3 >> 16) & 0xFFu;
             ipn++; mlen += (int)b;
-            while (b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { b = ldb<G>(src + ipn); ipn++; mlen += (int)b; }
+            while (b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { b = mem.b(ipn); ipn++; mlen += (int)b; }
             if (b == 255u || ipn > nI - 4) { stop = 1; kind = SP_END; break; }
         }
         const uint32_t opn = fop + (uint32_t)lit;
@@ -114,8 +114,8 @@ SC_FN void sp_walk(const uint8_t* __restrict__ src, int nI, int capI, int from, 
 }
 
 /* ---- phase 0: segments + first speculative walk ---- */
-template <bool G>
-SC_FN void sp_phase0(int lane, int nl, SpLane& L, SpShared& S, const uint8_t* src, int nI, int capI)
+template <class M>
+SC_FN void sp_phase0(int lane, int nl, SpLane& L, SpShared& S, M& mem, int nI, int capI)
 {
     const int lim = nI - 26;                                   /* last token position of the front region */
     int seg = (lim + nl) / nl;
@@ -125,7 +125,7 @@ SC_FN void sp_phase0(int lane, int nl, SpLane& L, SpShared& S, const uint8_t* sr
     L.from = L.segStart;
     L.isVoid = 0;
     SpEnd unused;
-    sp_walk<G, false>(src, nI, capI, L.from, L.segEnd, 0u, 0u, nullptr, 0u, S.res[lane], unused);
+    sp_walk<M, false>(mem, nI, capI, L.from, L.segEnd, 0u, 0u, nullptr, 0u, S.res[lane], unused);
     if (lane == 0) S.changed = 0;
 }
 
@@ -141,8 +141,8 @@ SC_FN void sp_decide(int lane, SpLane& L, const SpShared& S)
 }
 
 /* ---- fix-up round, part 2 (write): walk again from the new entry ---- */
-template <bool G>
-SC_FN void sp_redo(int lane, SpLane& L, SpShared& S, const uint8_t* src, int nI, int capI)
+template <class M>
+SC_FN void sp_redo(int lane, SpLane& L, SpShared& S, M& mem, int nI, int capI)
 {
     if (!L.need) return;
     L.from = L.newFrom;
@@ -151,24 +151,24 @@ SC_FN void sp_redo(int lane, SpLane& L, SpShared& S, const uint8_t* src, int nI,
         S.res[lane].exitPos = L.from; S.res[lane].stop = 1; S.res[lane].count = 0; S.res[lane].olen = 0;
     } else {
         SpEnd unused;
-        sp_walk<G, false>(src, nI, capI, L.from, L.segEnd, 0u, 0u, nullptr, 0u, S.res[lane], unused);
+        sp_walk<M, false>(mem, nI, capI, L.from, L.segEnd, 0u, 0u, nullptr, 0u, S.res[lane], unused);
     }
     S.changed = 1;
 }
 
 /* ---- WRITE pass; seqBase / outBase = exclusive sums of res[].count / res[].olen over the lanes before this one ---- */
-template <bool G>
-SC_FN void sp_write(int lane, const SpLane& L, SpShared& S, const uint8_t* src, int nI, int capI,
+template <class M>
+SC_FN void sp_write(int lane, const SpLane& L, SpShared& S, M& mem, int nI, int capI,
                     uint32_t seqBase, uint32_t outBase, uint32_t* marks, uint32_t markCap)
 {
     if (L.isVoid) { S.end[lane].kind = SP_RAN; return; }
     SpRes unused;
-    sp_walk<G, true>(src, nI, capI, L.from, L.segEnd, outBase, seqBase, marks, markCap, unused, S.end[lane]);
+    sp_walk<M, true>(mem, nI, capI, L.from, L.segEnd, outBase, seqBase, marks, markCap, unused, S.end[lane]);
 }
 
 /* ---- the first lane whose walk ended (`first` = smallest lane with end[].kind != SP_RAN, or nl - 1) finishes the block ---- */
-template <bool G>
-SC_FN void sp_finish(int lane, int first, SpShared& S, const uint8_t* src, int nI, int capI, uint32_t* marks, uint32_t markCap)
+template <class M>
+SC_FN void sp_finish(int lane, int first, SpShared& S, M& mem, int nI, int capI, uint32_t* marks, uint32_t markCap)
 {
     if (lane != first) return;
     const SpEnd e = S.end[first];
@@ -177,7 +177,7 @@ SC_FN void sp_finish(int lane, int first, SpShared& S, const uint8_t* src, int n
     st.ip = e.ip; st.op = (int64_t)e.op; st.nseq = e.nseq; st.fast = true;
     st.nextPrefetch = (e.nextEvt > 0) ? (int64_t)e.nextEvt + 128 : 128;
     uint32_t ns = 0;
-    S.ret = scan_tail<G>(src, nI, capI, st, &ns, marks, markCap);
+    S.ret = scan_tail(mem, nI, capI, st, &ns, marks, markCap);
     S.nseq = ns;
 }
 

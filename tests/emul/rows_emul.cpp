@@ -23,7 +23,8 @@ extern "C" int rows_emulate(const uint8_t* comp, int n, int cap, uint8_t* out, i
     if (n <= 0 || n > 65535 || cap <= 0 || cap > 65536 || head < 0 || head > 15 || rpt < 1) return -1000000;
     std::vector<uint32_t> marks(kMaxSeqFast, 0);
     uint32_t nseqU = 0;
-    const int total = scan_block<true>(comp, n, cap, &nseqU, marks.data(), (uint32_t)kMaxSeqFast);
+    MemPtr<true> mem{comp};
+    const int total = scan_block(mem, n, cap, &nseqU, marks.data(), (uint32_t)kMaxSeqFast);
     if (total <= 0) return total;
     const int nseq = (int)nseqU;
     stats[4] = nseq;

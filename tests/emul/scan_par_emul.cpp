@@ -15,15 +15,16 @@ extern "C" int scan_par_host(const uint8_t* src, int n, int cap, uint32_t* nSeqO
     const uint32_t markCap = (uint32_t)kMaxSeqFast;
     *nSeqOut = 0;
     stats[0] = stats[1] = 0; stats[2] = -1;
-    if (cap < 64 || n < kSpMinBytes) return scan_block<true>(src, n, cap, nSeqOut, marks, markCap);   // lane 0, one-thread scan
+    MemPtr<true> mem{src};
+    if (cap < 64 || n < kSpMinBytes) return scan_block(mem, n, cap, nSeqOut, marks, markCap);   // lane 0, one-thread scan
     static SpShared S;
     static SpLane L[kSpMaxLanes];
     memset(&S, 0, sizeof(S));
-    for (int l = 0; l < nl; l++) sp_phase0<true>(l, nl, L[l], S, src, n, cap);
+    for (int l = 0; l < nl; l++) sp_phase0(l, nl, L[l], S, mem, n, cap);
     for (;;) {
         for (int l = 0; l < nl; l++) sp_decide(l, L[l], S);
         S.changed = 0;
-        for (int l = 0; l < nl; l++) { if (L[l].need && !L[l].newVoid) stats[1]++; sp_redo<true>(l, L[l], S, src, n, cap); }
+        for (int l = 0; l < nl; l++) { if (L[l].need && !L[l].newVoid) stats[1]++; sp_redo(l, L[l], S, mem, n, cap); }
         if (!S.changed) break;
         stats[0]++;
         if (stats[0] > 2 * nl) return -1000000;                // must converge within nl rounds
@@ -31,12 +32,12 @@ extern "C" int scan_par_host(const uint8_t* src, int n, int cap, uint32_t* nSeqO
     uint32_t cb = 0, ob = 0;
     int first = nl - 1;
     for (int l = 0; l < nl; l++) {
-        sp_write<true>(l, L[l], S, src, n, cap, cb, ob, marks, markCap);
+        sp_write(l, L[l], S, mem, n, cap, cb, ob, marks, markCap);
         cb += S.res[l].count; ob += S.res[l].olen;
     }
     for (int l = nl - 1; l >= 0; l--) if (S.end[l].kind != SP_RAN) first = l;
     S.ret = -2000000;
-    for (int l = 0; l < nl; l++) sp_finish<true>(l, first, S, src, n, cap, marks, markCap);
+    for (int l = 0; l < nl; l++) sp_finish(l, first, S, mem, n, cap, marks, markCap);
     stats[2] = first;
     *nSeqOut = S.nseq;
     return S.ret;
@@ -77,7 +78,8 @@ extern "C" long long scan_par_fuzz(const uint8_t* base, int n, int rawSize, int 
         uint32_t ns1 = 0, ns2 = 0;
         int st[3];
         for (int i = 0; i < kMaxSeqFast; i++) { m1[i] = 0xABABABABu; m2[i] = 0xABABABABu; }
-        const int r1 = scan_block<true>(p, (int)len, cap, &ns1, wm ? m1 : nullptr, (uint32_t)kMaxSeqFast);
+        MemPtr<true> memP{p};
+        const int r1 = scan_block(memP, (int)len, cap, &ns1, wm ? m1 : nullptr, (uint32_t)kMaxSeqFast);
         const int r2 = scan_par_host(p, (int)len, cap, &ns2, wm ? m2 : nullptr, st);
         const uint32_t k = ns1 < (uint32_t)kMaxSeqFast ? ns1 : (uint32_t)kMaxSeqFast;
         if (r1 != r2 || (r1 > 0 && ns1 != ns2) || (r1 > 0 && wm && memcmp(m1, m2, sizeof(uint32_t) * k) != 0)) bad = -(1 + (long long)it);

@@ -17,8 +17,10 @@ from oracle.pyoracle import Oracle, Reference, have_reference
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def scan(tmp_path_factory):
+@pytest.fixture(scope="module", params=["plain", "ring"])
+def scan(request, tmp_path_factory):
+    """plain: reads straight from the block (MemPtr).  ring: the same scan through the per-thread ring of the
+    device's scan kernel (MemRing); its host build delays every asynchronous copy to the matching wait."""
     gxx = shutil.which("g++")
     if not gxx:
         pytest.skip("g++ not available")
@@ -28,18 +30,21 @@ def scan(tmp_path_factory):
     lib = C.CDLL(so)
     lib.scan_host.restype = C.c_int
     lib.scan_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
+    lib.scan_host_ring.restype = C.c_int
+    lib.scan_host_ring.argtypes = lib.scan_host.argtypes
+    entry = lib.scan_host if request.param == "plain" else lib.scan_host_ring
     max_seq = lib.scan_host_max_seq()
 
     def run(block, cap, shift=0, want_marks=True):
-        """-> (ret, nseq, marks[:min(nseq, max)])  block placed at byte offset 8+shift of an aligned buffer"""
+        """-> (ret, nseq, marks[:min(nseq, max)])  block placed at byte offset 16+shift of a 16-byte aligned buffer"""
         n = len(block)
-        buf = np.full(n + 32, 0xEE, dtype=np.uint8)
+        buf = np.full(n + 80, 0xEE, dtype=np.uint8)
         base = buf.ctypes.data
-        pad = (-base) % 8 + 8 + shift
+        pad = (-base) % 16 + 16 + shift
         buf[pad:pad + n] = np.frombuffer(bytes(block), dtype=np.uint8)
         marks = np.zeros(max_seq, dtype=np.uint32)
         ns = C.c_uint32(0)
-        r = lib.scan_host(base + pad, n, cap, C.byref(ns), marks.ctypes.data if want_marks else None)
+        r = entry(base + pad, n, cap, C.byref(ns), marks.ctypes.data if want_marks else None)
         return r, ns.value, marks[:min(ns.value, max_seq)].copy()
     run.max_seq = max_seq
     return run
@@ -81,7 +86,7 @@ def test_golden_decode_vectors(scan):
     assert len(cases) > 1000
     for i, c in enumerate(cases):
         blk = bytes.fromhex(c["block"])
-        r, ns, _ = scan(blk, c["cap"], shift=i % 4)
+        r, ns, _ = scan(blk, c["cap"], shift=i % 16)
         assert r == c["ret"], (i, c["cap"], r, c["ret"])
         if r <= 0:
             assert ns == 0 or r == 0
@@ -89,7 +94,7 @@ def test_golden_decode_vectors(scan):
 
 def test_fixture_block_marks(scan):
     blk = open(os.path.join(HERE, "golden", "p50_seed0_64k.lz4block"), "rb").read()
-    for shift in range(4):
+    for shift in range(16):
         r, ns, marks = scan(blk, 65536, shift)
         want = true_marks(blk)
         assert r == 65536 and ns == len(want)
@@ -111,7 +116,7 @@ def test_valid_and_corrupted_blocks_vs_oracle(scan):
             _, comp = orc.compress(raw, 1)
             comp = bytes(comp)
             for cap in {size, size + 1, size + 64, size + 100, max(size - 1, 0), max(size - 70, 0), size // 2}:
-                r, ns, marks = scan(comp, cap, shift=int(rng.integers(0, 4)))
+                r, ns, marks = scan(comp, cap, shift=int(rng.integers(0, 16)))
                 want, _ = orc.decompress(comp, cap)
                 assert r == want, (proba, size, cap, r, want)
                 if r > 0:
@@ -135,7 +140,7 @@ def test_valid_and_corrupted_blocks_vs_oracle(scan):
                     else:
                         b[pos:pos] = bytes(rng.integers(0, 256, int(rng.integers(1, 4)), dtype=np.uint8))
                 cap = int(rng.choice([size, size + 64, size + 1000, max(size - 5, 0)]))
-                r, ns, _ = scan(bytes(b), cap, shift=int(rng.integers(0, 4)))
+                r, ns, _ = scan(bytes(b), cap, shift=int(rng.integers(0, 16)))
                 want, _ = orc.decompress(bytes(b), cap)
                 assert r == want, (proba, size, cap, r, want)
                 bad += want < 0
