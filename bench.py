@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--chunks", type=int, default=4, help="N > 1: pieces of a rank's shard whose exchange overlaps the decode of the next piece")
     return ap.parse_args()
 
 
@@ -176,7 +177,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": round(1e3 * med, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(n_blocks, gib, args.proba, args.accel, nbytes / float(csz.sum())),
+        "config": workload_config(n_blocks, gib, args.proba, args.accel, nbytes / float(csz.sum()), args.gpus),
         "timing": {"value_from": "median step", "best_GBps": round(nbytes / best / GB, 3),
                    "median_GBps": round(value, 3), "mean_GBps": round(nbytes / mean / GB, 3),
                    "spread": round(max(times) / best, 3)},
@@ -193,12 +194,17 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_blocks, gib, proba, accel, ratio):
-    """`config` of the JSON line: identical text for both arms (the driver compares it)."""
+def workload_config(n_blocks, gib, proba, accel, ratio, gpus):
+    """`config` of the JSON line: identical for both arms (the driver compares it)."""
     return {"workload": "decompress-only, %d independent %d KB blocks per GPU (%.2f GiB), tests/datagen P%d "
                         "(RDG_genBuffer per 64 MiB segment, seed=rank*64+k), compressed by LZ4_compress_fast accel %d"
                         % (n_blocks, BLOCK // 1024, gib, round(proba * 100), accel),
-            "block_bytes": BLOCK, "blocks_per_gpu": n_blocks, "ratio": round(ratio, 4)}
+            "block_bytes": BLOCK, "blocks_per_gpu": n_blocks, "ratio": round(ratio, 2),
+            "l2": "the inputs of a step (%.1f GiB compressed + %.1f GiB decoded) exceed the 126 MB L2 and every CPU cache; no flush needed"
+                  % (n_blocks * BLOCK / ratio / (1 << 30), n_blocks * BLOCK / (1 << 30)),
+            "parallelism": "blocks partitioned contiguously over %d rank(s); for N > 1 the timed step ends with the exchange "
+                           "of the decoded shards (every rank holds the whole frame), overlapped chunk by chunk with the decode"
+                           % gpus}
 
 
 # --------------------------------------------------------------------------------------------
@@ -266,17 +272,37 @@ def run_ours(args):
     total = n_blocks * BLOCK
     seed0 = rank * 64                           # seed = rank*64 + k
     host = orc.datagen_mt(total, SEG, args.proba, seed0, max(1, cores // world))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"
 
-    # ---- setup (untimed): upload, compress ON THE GPU (byte-identical to the reference), pack ----
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+
+    # ---- compress leg (BASELINE config 3): ON THE GPU, byte-identical to the reference; timed with its own clocks ----
     src = torch.from_numpy(host).to(device)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     slots, csizes, stride = batch.compress_blocks(src, BLOCK, args.accel)      # warm-up + result
     torch.cuda.synchronize()
+    KC = max(1, min(args.steps, 3))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tc0 = time.time()
     ev0.record()
-    batch.compress_blocks(src, BLOCK, args.accel, slots=slots, out_sizes=csizes)
+    for _ in range(KC):
+        batch.compress_blocks(src, BLOCK, args.accel, slots=slots, out_sizes=csizes)
     ev1.record()
     torch.cuda.synchronize()
-    compress_ms = ev0.elapsed_time(ev1)
+    tc1 = time.time()
+    compress_ms = ev0.elapsed_time(ev1) / KC
+    compress_clocks = sampler.summary(tc0, tc1)
     packed, offs_all = batch.pack_blocks(slots, stride, csizes)
     offs = offs_all[:-1].contiguous()
     torch.cuda.synchronize()
@@ -284,8 +310,7 @@ def run_ours(args):
     csz_host = csizes.cpu().numpy()
     # checker: a sample of GPU-compressed blocks must equal the oracle's bytes
     rng = np.random.default_rng(rank)
-    slots_sample = rng.integers(0, n_blocks, 8)
-    for i in slots_sample:
+    for i in rng.integers(0, n_blocks, 8):
         eret, eout = orc.compress(host[i * BLOCK:(i + 1) * BLOCK], args.accel)
         got = slots[i * stride:i * stride + int(csz_host[i])].cpu().numpy().tobytes()
         assert int(csz_host[i]) == eret and got == eout, "GPU compressor differs from the oracle at block %d" % i
@@ -293,52 +318,78 @@ def run_ours(args):
     del slots
     torch.cuda.empty_cache()
 
-    out = torch.empty(total, dtype=torch.uint8, device=device)
+    # decoded frame: every rank decodes INTO ITS SLICE of the full buffer (N > 1: the exchange fills the rest)
+    full = torch.empty(world * total, dtype=torch.uint8, device=device)
+    out = full[rank * total:(rank + 1) * total]
     rets = torch.empty(n_blocks, dtype=torch.int32, device=device)
-    ws = torch.empty(int(lib.LZ4B200_decompress_workspace_bytes(n_blocks)), dtype=torch.uint8, device=device)
+    ws = torch.empty(int(lib.LZ4B200_decompress_workspace_bytes_for(n_blocks, 0, BLOCK)), dtype=torch.uint8, device=device)
 
-    def step(phases=3):
-        batch.decompress_blocks(packed, offs, csizes, BLOCK, out=out, out_sizes=rets, workspace=ws, phases=phases)
+    def decode(lo=0, hi=n_blocks, phases=3):
+        batch.decompress_blocks(packed, offs[lo:hi], csizes[lo:hi], BLOCK, out=out[lo * BLOCK:hi * BLOCK],
+                                out_sizes=rets[lo:hi], workspace=ws, phases=phases)
+
+    def step():
+        """one pass of the hot path over this rank's batch; N > 1: + the exchange of the decoded shards, overlapped"""
+        if world == 1:
+            decode()
+        else:
+            ldist.decode_and_allgather(full, n_blocks, BLOCK, decode, n_chunks=args.chunks)
 
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     assert bool((rets == BLOCK).all()) and torch.equal(out, src), "GPU decode mismatch"
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    gather_ok = None
+    if world > 1:                               # every rank's shard arrived: compare against regenerated neighbours
+        nb = (rank + 1) % world
+        other = orc.datagen_mt(SEG, SEG, args.proba, nb * 64, max(1, cores // world))
+        gather_ok = bool(torch.equal(full[nb * total:nb * total + SEG].cpu(), torch.from_numpy(other)))
+        assert gather_ok, "exchanged frame differs from the neighbour's data"
 
     # ---- timed region: K steps, device resident, CUDA events on the launching stream ----
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
     K = args.steps
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     launches0 = lib.LZ4B200_launch_count()
     barrier(); torch.cuda.synchronize()
     t_wall0 = time.time()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for k in range(K):
-        evs[k][0].record()
-        step(1)                      # scan kernel
-        evs[k][1].record()
-        step(2)                      # expand kernel (dominant)
-        evs[k][2].record()
+        step()
     end.record()
     torch.cuda.synchronize(); barrier()
     t_wall1 = time.time()
     launches = lib.LZ4B200_launch_count() - launches0
-    elapsed_ms = start.elapsed_time(end)
-    scan_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
-    expand_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+    my_ms = start.elapsed_time(end)
+    elapsed_ms = my_ms
+    per_rank_ms = None
     if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+        t = torch.zeros(world, dtype=torch.float64, device=device)
+        t[rank] = my_ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        per_rank_ms = [round(float(x) / K, 4) for x in t.tolist()]
+        elapsed_ms = float(t.max().item())
     value = world * total * K / (elapsed_ms * 1e-3) / GB
     clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- the two kernels of the decode, timed separately (same launches, events between the phases) ----
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    barrier(); torch.cuda.synchronize()
+    for k in range(K):
+        evs[k][0].record()
+        decode(phases=1)             # scan kernel
+        evs[k][1].record()
+        decode(phases=2)             # expand kernel (dominant)
+        evs[k][2].record()
+    torch.cuda.synchronize()
+    scan_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
+    expand_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+    codec_ms = sum(e[0].elapsed_time(e[2]) for e in evs) / K
+    if world > 1:
+        t = torch.tensor([codec_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        codec_ms_max = float(t.item())
+    else:
+        codec_ms_max = codec_ms
 
     # ---- e2e: same workload through the host-buffer C-ABI call, pinned host memory ----
     e2e = None
@@ -372,34 +423,30 @@ def run_ours(args):
         e2e = {"value": round(world * total * args.e2e_steps / dt / GB, 3), "unit": "GB/s",
                "pcie_pinned_copy_GBps": pcie, "host_numa_binding": numa,
                "h2d_bytes_per_step": int(comp_bytes + n_blocks * 12), "d2h_bytes_per_step": int(total + n_blocks * 4),
-               "steps": args.e2e_steps, "api": "LZ4B200_decompress_blocks_host (pinned host buffers)"}
+               "steps": args.e2e_steps, "api": "LZ4B200_decompress_blocks_host (pinned host buffers)",
+               "ceiling": "PCIe: %.1f GB of output per step cannot leave the GPU faster than the pinned D2H rate (%.1f GB/s), "
+                          "so e2e <= that rate whatever the kernels do" % (total / GB, pcie["d2h"])}
         del h_comp, h_out
         os.sched_setaffinity(0, all_cpus)
     sampler.stop()
 
-    # ---- reassembly (multi-GPU only): one in-place NCCL all-gather of the decoded shards ----
-    gather = None
-    if world > 1 and not args.no_gather:
-        full = torch.empty(world * total, dtype=torch.uint8, device=device)
-        mine = full[rank * total:(rank + 1) * total]
-        for _ in range(2):
-            batch.decompress_blocks(packed, offs, csizes, BLOCK, out=mine, out_sizes=rets, workspace=ws)
-            ldist.allgather_decoded(full, world * n_blocks, BLOCK)
+    # ---- compressed-side reassembly on NCCL (N > 1): size table + padded shards, verified ----
+    comp_gather = None
+    if world > 1:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ldist.allgather_compressed(packed, comp_bytes, csizes)
         torch.cuda.synchronize(); barrier()
-        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         g0.record()
-        batch.decompress_blocks(packed, offs, csizes, BLOCK, out=mine, out_sizes=rets, workspace=ws)
+        all_sizes, shards, shard_bytes = ldist.allgather_compressed(packed, comp_bytes, csizes)
         g1.record()
-        ldist.allgather_decoded(full, world * n_blocks, BLOCK)
-        g2.record()
         torch.cuda.synchronize()
-        t = torch.tensor([g0.elapsed_time(g1), g1.elapsed_time(g2), g0.elapsed_time(g2)], dtype=torch.float64, device=device)
+        ok = bool(torch.equal(all_sizes[rank * n_blocks:(rank + 1) * n_blocks], csizes)) and \
+            bool(torch.equal(shards[rank, :comp_bytes], packed[:comp_bytes])) and int(shard_bytes[rank]) == comp_bytes
+        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ok = bool(torch.equal(full[rank * total:(rank + 1) * total], src))
-        gather = {"decode_ms": round(float(t[0]), 3), "allgather_ms": round(float(t[1]), 3),
-                  "GBps_with_allgather": round(world * total / (float(t[2]) * 1e-3) / GB, 3),
-                  "allgather_bytes_per_rank": int((world - 1) * total), "verified": ok}
-        del full
+        comp_gather = {"ms": round(float(t.item()), 3), "bytes_in_per_rank": int(shard_bytes.sum().item()) - comp_bytes,
+                       "verified": ok}
+        del shards
 
     # ---- cpu baseline (rank 0, N == 1): the reference's CPU path on a bounded sample ----
     cpu = None
@@ -423,47 +470,54 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
     algo_bytes = comp_bytes + total                      # C_i read once + U_i written once
     achieved = algo_bytes / (expand_ms * 1e-3) / GB
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("expand_dram_bytes_per_launch")
-    except (OSError, ValueError):
+    step_achieved = algo_bytes / (codec_ms * 1e-3) / GB
+    traffic, step_traffic, traffic_src = None, None, None
+    try:                                                 # ncu --set full captures, summarised per 64 KB block by profiles/summarize.py
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if abs(args.proba - tj.get("proba", 0.5)) < 1e-9 and BLOCK == tj.get("block_bytes", 65536):
+            traffic = int(tj["expand_dram_bytes_per_block"] * n_blocks)
+            step_traffic = int((tj["expand_dram_bytes_per_block"] + tj["scan_dram_bytes_per_block"]) * n_blocks)
+            traffic_src = tj.get("source")
+    except (OSError, ValueError, KeyError):
         pass
+    config = workload_config(n_blocks, args.gib, args.proba, args.accel, total / comp_bytes, world)
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": K,
         "warmup": max(args.warmup, 3), "ms_per_step": round(elapsed_ms / K, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "decompress-only, %d independent %d KB blocks per GPU (%.2f GiB), tests/datagen P%d "
-                               "(RDG_genBuffer per 64 MiB segment, seed=rank*64+k), compressed by LZ4_compress_fast accel %d"
-                               % (n_blocks, BLOCK // 1024, args.gib, round(args.proba * 100), args.accel),
-                   "block_bytes": BLOCK, "blocks_per_gpu": n_blocks, "ratio": round(total / comp_bytes, 4),
-                   "l2": "inputs (%.1f GiB compressed + %.1f GiB output per step) exceed the 126 MB L2; no flush needed"
-                         % (comp_bytes / (1 << 30), total / (1 << 30)),
-                   "parallelism": "blocks sharded contiguously, %d rank(s), no collective in the timed region" % world},
+        "config": config,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic,
-                     "kernel": "lz4_expand kernel", "kernel_ms": round(expand_ms, 4), "scan_kernel_ms": round(scan_ms, 4),
+                     "kernel": "lz4_expand_rows_kernel", "kernel_ms": round(expand_ms, 4), "scan_kernel_ms": round(scan_ms, 4),
                      "algorithmic_bytes_per_launch": algo_bytes,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+                     "step": {"kernels": "lz4_scan_kernel + lz4_expand_rows_kernel (+ the empty generic expand launch)",
+                              "ms": round(codec_ms, 4), "achieved": round(step_achieved, 2),
+                              "frac": round(step_achieved / peak, 4), "traffic": step_traffic},
+                     "traffic_source": traffic_src,
+                     "peak_source": peak_source},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "compress": {"GBps": round(total / (compress_ms * 1e-3) / GB, 3), "ms": round(compress_ms, 3),
-                     "ratio": round(total / comp_bytes, 4), "accel": args.accel,
-                     "note": "setup leg: byte-identical to LZ4_compress_fast (sample checked against the oracle)"},
+                     "ratio": round(total / comp_bytes, 4), "accel": args.accel, "steps": KC,
+                     "kernel": "lz4_encode_kernel (byte-identical to LZ4_compress_fast; sample checked against the oracle)",
+                     "roofline": {"bound": "hbm", "achieved": round(algo_bytes / (compress_ms * 1e-3) / GB, 2), "peak": peak,
+                                  "unit": "GB/s", "frac": round(algo_bytes / (compress_ms * 1e-3) / GB / peak, 4)},
+                     "clocks": compress_clocks},
     }
+    if world > 1:
+        line["multi_gpu"] = {"value_includes": "decode + exchange of the decoded shards (grouped NCCL send/recv per chunk, "
+                                               "%d chunks, exchange of chunk k overlaps the decode of chunk k+1)" % args.chunks,
+                             "per_rank_ms_per_step": per_rank_ms,
+                             "codec_only": {"ms_per_step_max_over_ranks": round(codec_ms_max, 4),
+                                            "GBps": round(world * total / (codec_ms_max * 1e-3) / GB, 3)},
+                             "exchange_bytes_in_per_rank": int((world - 1) * total), "exchange_verified": gather_ok,
+                             "compressed_reassembly": comp_gather}
     if e2e:
         line["e2e"] = e2e
     if cpu:
         line["cpu_baseline"] = cpu
-    if gather:
-        line["reassembly"] = gather
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

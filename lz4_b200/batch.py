@@ -8,9 +8,22 @@ import torch
 from . import _lib
 
 
-def _stream_ptr(stream=None):
-    s = stream if stream is not None else torch.cuda.current_stream()
-    return s.cuda_stream
+def _stream(stream=None):
+    return stream if stream is not None else torch.cuda.current_stream()
+
+
+_workspaces = {}        # device index -> cached decode workspace (grown on demand, reused by later calls)
+
+
+def _workspace(device, nbytes, stream):
+    """One workspace per device, allocated on the launch stream: calls on the same stream are ordered by the
+    stream; a caller that decodes on several streams at once passes its own `workspace`."""
+    ws = _workspaces.get(device.index)
+    if ws is None or ws.numel() < nbytes:
+        with torch.cuda.stream(stream):
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[device.index] = ws
+    return ws
 
 
 def _need_cuda(*ts):
@@ -35,18 +48,20 @@ def decompress_blocks(comp, offsets, sizes, block_capacity, out=None, out_stride
     _need_cuda(comp, offsets, sizes, out)
     n = int(sizes.numel())
     stride = int(out_stride if out_stride is not None else block_capacity)
-    if out is None:
-        out = torch.empty(n * stride, dtype=torch.uint8, device=comp.device)
-    if out_sizes is None:
-        out_sizes = torch.empty(n, dtype=torch.int32, device=comp.device)
-    ws_bytes = int(lib.LZ4B200_decompress_workspace_bytes(n))
+    st = _stream(stream)
+    with torch.cuda.stream(st):                     # temporaries belong to the stream the kernels run on
+        if out is None:
+            out = torch.empty(n * stride, dtype=torch.uint8, device=comp.device)
+        if out_sizes is None:
+            out_sizes = torch.empty(n, dtype=torch.int32, device=comp.device)
+    ws_bytes = int(lib.LZ4B200_decompress_workspace_bytes_for(n, 0, int(block_capacity)))
     if workspace is None or workspace.numel() < ws_bytes:
-        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=comp.device)
+        workspace = _workspace(comp.device, ws_bytes, st)
     assert offsets.dtype == torch.int64 and sizes.dtype == torch.int32 and comp.dtype == torch.uint8
     rc = lib.LZ4B200_decompress_blocks_phased(comp.data_ptr(), offsets.data_ptr(), sizes.data_ptr(), out.data_ptr(),
                                               None, stride, None, int(block_capacity), out_sizes.data_ptr(), n,
                                               workspace.data_ptr(), workspace.numel(), int(phases),
-                                              _stream_ptr(stream))
+                                              st.cuda_stream)
     _lib.check(rc, "LZ4B200_decompress_blocks")
     return out, out_sizes
 
@@ -55,7 +70,7 @@ def compress_blocks(src, block_size, acceleration=1, slots=None, slot_stride=Non
                     out_sizes=None, src_sizes=None, stream=None):
     """Compress src (u8 device tensor) as ceil(len/block_size) independent blocks.
 
-    Returns (slots, out_sizes): block i's bytes are slots[i*slot_stride : i*slot_stride+out_sizes[i]].
+    Returns (slots, out_sizes, slot_stride): block i's bytes are slots[i*slot_stride : i*slot_stride+out_sizes[i]].
     """
     lib = _lib.load()
     _need_cuda(src, slots)
@@ -63,16 +78,18 @@ def compress_blocks(src, block_size, acceleration=1, slots=None, slot_stride=Non
     n = (total + block_size - 1) // block_size if total else 0
     cap = int(slot_capacity if slot_capacity is not None else compress_bound(block_size))
     stride = int(slot_stride if slot_stride is not None else ((cap + 15) // 16) * 16)
-    if slots is None:
-        slots = torch.empty(max(n, 1) * stride, dtype=torch.uint8, device=src.device)
-    if out_sizes is None:
-        out_sizes = torch.empty(max(n, 1), dtype=torch.int32, device=src.device)
-    if src_sizes is None and n and total != n * block_size:
-        src_sizes = torch.full((n,), block_size, dtype=torch.int32, device=src.device)
-        src_sizes[-1] = total - (n - 1) * block_size
+    st = _stream(stream)
+    with torch.cuda.stream(st):
+        if slots is None:
+            slots = torch.empty(max(n, 1) * stride, dtype=torch.uint8, device=src.device)
+        if out_sizes is None:
+            out_sizes = torch.empty(max(n, 1), dtype=torch.int32, device=src.device)
+        if src_sizes is None and n and total != n * block_size:
+            src_sizes = torch.full((n,), block_size, dtype=torch.int32, device=src.device)
+            src_sizes[-1] = total - (n - 1) * block_size
     rc = lib.LZ4B200_compress_blocks(src.data_ptr(), int(block_size), src_sizes.data_ptr() if src_sizes is not None else None,
                                      int(block_size), slots.data_ptr(), stride, cap, int(acceleration),
-                                     out_sizes.data_ptr(), n, _stream_ptr(stream))
+                                     out_sizes.data_ptr(), n, st.cuda_stream)
     _lib.check(rc, "LZ4B200_compress_blocks")
     return slots, out_sizes[:n], stride
 
@@ -82,10 +99,12 @@ def pack_blocks(slots, slot_stride, sizes, header_bytes=0, packed=None, stream=N
     lib = _lib.load()
     _need_cuda(slots, sizes)
     n = int(sizes.numel())
-    offsets = torch.empty(n + 1, dtype=torch.int64, device=slots.device)
-    if packed is None:
-        packed = torch.empty(n * (int(slot_stride) + header_bytes) + 16, dtype=torch.uint8, device=slots.device)
+    st = _stream(stream)
+    with torch.cuda.stream(st):
+        offsets = torch.empty(n + 1, dtype=torch.int64, device=slots.device)
+        if packed is None:
+            packed = torch.empty(n * (int(slot_stride) + header_bytes) + 16, dtype=torch.uint8, device=slots.device)
     rc = lib.LZ4B200_pack_blocks(slots.data_ptr(), int(slot_stride), sizes.data_ptr(), n, packed.data_ptr(),
-                                 offsets.data_ptr(), int(header_bytes), _stream_ptr(stream))
+                                 offsets.data_ptr(), int(header_bytes), st.cuda_stream)
     _lib.check(rc, "LZ4B200_pack_blocks")
     return packed, offsets

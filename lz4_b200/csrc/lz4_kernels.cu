@@ -74,6 +74,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+/* wait for the phase with the given parity; the hardware may suspend the warp for up to `hintNs` per attempt, so that
+ * waiting warps do not take issue slots from the warps they are waiting for */
+#ifndef LZ4K_WAIT_HINT_NS
+#define LZ4K_WAIT_HINT_NS 2000
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)LZ4K_WAIT_HINT_NS) : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
@@ -520,7 +533,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
         }
         __syncthreads();                                   /* rows are zero */
         PHASE_MARK(0);                                     // zeroing + marks
-        while (!mbar_try_wait(&S.mbar, parity)) { }
+        mbar_wait(&S.mbar, parity);
         parity ^= 1;
         PHASE_MARK(1);                                     // TMA load wait
 
@@ -608,7 +621,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
             };
             resolve(0);
             for (int wv = 0; wv < nWaves; wv++) {
-                if (wv > 0) { while (!mbar_try_wait(&S.wbar, wpar)) { } wpar ^= 1; }   /* every warp has copied wave wv-1 */
+                if (wv > 0) { mbar_wait(&S.wbar, wpar); wpar ^= 1; }   /* every warp has copied wave wv-1 */
                 const uint32_t p0 = (uint32_t)(wv * kWave + tid);
                 const uint32_t lim = ((wv + 1) * kWave <= total) ? 0xFFFFFFFFu : (uint32_t)total;
                 uint32_t v[kRowsRpt];
@@ -622,7 +635,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
                 if (lane == 0) mbar_arrive(&S.wbar);           /* release: this warp's bytes of wave wv are written */
                 if (wv + 1 < nWaves) resolve(wv + 1);
             }
-            while (!mbar_try_wait(&S.wbar, wpar)) { }
+            mbar_wait(&S.wbar, wpar);
             wpar ^= 1;
             PHASE_MARK(5);                                     // waves
         }

@@ -248,37 +248,48 @@ template <class M> SC_FN bool scan_front(M& mem, int nIn, int capIn, ScanState& 
     uint32_t nseq = st.nseq;
     int fip = 0, fop = 0, nextEvt = 0;
     const int nI = nIn, capI = capIn;
+    /* The 32 lanes of a warp walk 32 unrelated blocks, so every data-dependent branch splits the warp and the
+     * walk's time is (instructions issued per step, all paths of all lanes) x (latency of a dependent instruction).
+     * The body is therefore straight-line code for every sequence whose lengths need at most two extension bytes
+     * (literal runs < 525 bytes, matches < 529); longer ones go round the reference's loops, which are skipped
+     * (condition false for every lane) otherwise.  The exits are collected and taken once, in the reference's order. */
     while (fip <= nI - 26) {
-        if (fip >= nextEvt) {                                      // L1 prefetch, once per 128 input bytes
+        if (M::kPrefetch && fip >= nextEvt) {                      // L1 prefetch, once per 128 input bytes
             if (fip + 128 < nI) mem.prefetch(fip + 128);
             nextEvt = ((fip >> 7) + 1) << 7;
         }
         MARK_VISIT(fip, fop);
         mem.ensure(fip);                                           // [fip, fip + kMemAhead) is readable: token, short literals, offset
-        const uint32_t v = mem.u32(fip);                       // token, then up to 3 bytes that follow it
-        const int mcode = (int)(v & 15u);
-        int lit = (int)((v >> 4) & 15u), q = 1;
-        if (lit == 15) {                                           // read_variable_length (lz4.c:2093), limit n-15
-            uint32_t b = (v >> 8) & 0xFFu;
-            lit += (int)b; q = 2;
-            while (b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { mem.ensure(fip + q); b = mem.b(fip + q); q++; lit += (int)b; }
-            if (b == 255u || fip + q > nI - 15) break;             // read limit / absurd run: replay byte-wise
-            if ((uint32_t)fop + (uint32_t)lit > (uint32_t)(capI - 32) ||                 // lz4.c:2104 -> safe_literal_copy
-                (uint32_t)(fip + q) + (uint32_t)lit + 32u > (uint32_t)nI) break;         // (unsigned: sums may pass 2^31)
-            mem.ensure(fip + q + lit);                             // a long literal run: the offset lies beyond the window
-        }
+        const uint32_t v = mem.u32(fip);                           // token, then the 3 bytes that follow it
+        const int mcode = (int)(v & 15u), lit4 = (int)((v >> 4) & 15u);
+        /* read_variable_length (lz4.c:2093), limit n-15: the first two extension bytes come with the token */
+        const bool e1 = (lit4 == 15);
+        const uint32_t l1 = (v >> 8) & 0xFFu, l2 = (v >> 16) & 0xFFu;
+        const bool e2 = e1 && l1 == 255u;                          // (fip + 2 <= nI - 15 holds: fip <= nI - 26)
+        int lit = lit4 + (e1 ? (int)l1 : 0) + (e2 ? (int)l2 : 0);
+        int q = 1 + (e1 ? 1 : 0) + (e2 ? 1 : 0);
+        uint32_t b = e2 ? l2 : l1;
+        while (e1 && b == 255u && fip + q <= nI - 15 && lit < (1 << 28)) { mem.ensure(fip + q); b = mem.b(fip + q); q++; lit += (int)b; }
+        const bool exitL = e1 && (b == 255u || fip + q > nI - 15 ||                      // read limit / absurd run: replay byte-wise
+                                  (uint32_t)fop + (uint32_t)lit > (uint32_t)(capI - 32) ||              // lz4.c:2104 -> safe_literal_copy
+                                  (uint32_t)(fip + q) + (uint32_t)lit + 32u > (uint32_t)nI);           // (unsigned: sums may pass 2^31)
         const int offPos = fip + q + lit;
-        const uint32_t v3 = mem.u32(offPos);                   // offset (LE16), then the first match-length byte
+        const int offRead = exitL ? fip : offPos;                  // an exiting lane must not read at a wild position
+        if (e1) mem.ensure(offRead);                               // a long literal run: the offset lies beyond the window
+        const uint32_t v3 = mem.u32(offRead);                      // offset (LE16), then the first two match-length bytes
         const int off16 = (int)(v3 & 0xFFFFu);
-        int mlen = mcode + kMinMatch, ipn = offPos + 2;
-        if (mcode == 15) {                                         // read_variable_length (lz4.c:2128), limit n-4
-            uint32_t b = (v3 >> 16) & 0xFFu;
-            ipn++; mlen += (int)b;
-            while (b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { mem.ensure(ipn); b = mem.b(ipn); ipn++; mlen += (int)b; }
-            if (b == 255u || ipn > nI - 4) break;
-        }
+        /* read_variable_length (lz4.c:2128), limit n-4 */
+        const bool m1 = (mcode == 15);
+        const uint32_t x1 = (v3 >> 16) & 0xFFu, x2 = v3 >> 24;
+        const bool m2 = m1 && x1 == 255u && offPos + 3 <= nI - 4;
+        int mlen = mcode + kMinMatch + (m1 ? (int)x1 : 0) + (m2 ? (int)x2 : 0);
+        int ipn = offPos + 2 + (m1 ? 1 : 0) + (m2 ? 1 : 0);
+        b = m2 ? x2 : x1;
+        while (!exitL && m1 && b == 255u && ipn <= nI - 4 && mlen < (1 << 28)) { mem.ensure(ipn); b = mem.b(ipn); ipn++; mlen += (int)b; }
+        const bool exitM = m1 && (b == 255u || ipn > nI - 4);
         const int opn = fop + lit;
-        if ((uint32_t)opn + (uint32_t)mlen >= (uint32_t)(capI - 64)) break;   // lz4.c:2137/2142 -> safe_match_copy
+        const bool exitC = (uint32_t)opn + (uint32_t)mlen >= (uint32_t)(capI - 64);   // lz4.c:2137/2142 -> safe_match_copy
+        if (exitL || exitM || exitC) break;
         if (off16 > opn) { st.ip = ipn; st.nseq = nseq; return false; }       // lz4.c:2161
         fip = ipn; fop = opn + mlen; nseq++;
     }

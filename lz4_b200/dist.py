@@ -43,6 +43,49 @@ def allgather_decoded(full, n_blocks, block_size, group=None):
     return _all_gather_flat(full[:world * per], shard, group)
 
 
+def chunk_ranges(n_units, n_chunks):
+    """[lo, hi) of each of n_chunks nearly equal contiguous pieces of range(n_units) (empty pieces dropped)."""
+    out = []
+    for k in range(n_chunks):
+        lo, hi = n_units * k // n_chunks, n_units * (k + 1) // n_chunks
+        if hi > lo:
+            out.append((lo, hi))
+    return out
+
+
+def decode_and_allgather(full, blocks_per_rank, block_size, decode_chunk, n_chunks=4, group=None):
+    """Decode this rank's shard chunk by chunk and exchange every chunk as soon as it is decoded, so that the
+    exchange of chunk k runs while chunk k+1 is being decoded (the ordered-writer role of lz4io.c:594-635, spread
+    over the ranks: afterwards every rank holds the whole decoded frame).
+
+    full            u8[world * blocks_per_rank * block_size]; rank r's shard is the r-th equal slice.
+    decode_chunk    decode_chunk(lo, hi): enqueue, on the CURRENT stream, the decode of this rank's blocks [lo, hi)
+                    into their final place in `full`.
+    Exchange of one chunk = one grouped send/recv (NCCL P2P over NVLink): every rank receives its peers' bytes
+    straight into their final place in `full` -- no staging buffer and no re-ordering copy, which a chunk-wise
+    ncclAllGather (contiguous output per call) would need.  The collective stream waits for the decode of chunk k
+    through the event torch.distributed records at issue time; the codec stream carries on with chunk k+1.
+    Returns the list of outstanding works (already waited for: the current stream is ordered after them)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = blocks_per_rank * block_size
+    works = []
+    for lo, hi in chunk_ranges(blocks_per_rank, n_chunks):
+        decode_chunk(lo, hi)
+        if world == 1:
+            continue
+        a, b = lo * block_size, hi * block_size
+        ops = []
+        for d in range(1, world):                              # peer order staggered per rank: no hot receiver
+            to, frm = (rank + d) % world, (rank - d) % world
+            ops.append(dist.P2POp(dist.isend, full[rank * per + a:rank * per + b], to, group))
+            ops.append(dist.P2POp(dist.irecv, full[frm * per + a:frm * per + b], frm, group))
+        works += dist.batch_isend_irecv(ops)
+    for wk in works:
+        wk.wait()
+    return works
+
+
 def allgather_compressed(packed, total_bytes, sizes, group=None):
     """Reassemble a compressed frame from per-rank packed shards.
 

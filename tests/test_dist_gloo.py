@@ -51,6 +51,22 @@ def _worker(rank, world, port, n_blocks, q):
         full[i * BLOCK:(i + 1) * BLOCK] = torch.from_numpy(np.frombuffer(out, dtype=np.uint8).copy())
     ldist.allgather_decoded(full, n_blocks, BLOCK)
     ok_dec = bool((full.numpy() == data).all())
+    # --- the overlapped form: decode chunk by chunk, exchange each chunk as soon as it is decoded ---
+    if n_blocks % world == 0:
+        full2 = torch.zeros(n_blocks * BLOCK, dtype=torch.uint8)
+        per = n_blocks // world
+        calls = []
+
+        def decode_chunk(a, b):
+            calls.append((a, b))
+            for j in range(a, b):
+                r, out = orc.decompress(chunks[j], BLOCK)
+                assert r == BLOCK
+                i = rank * per + j
+                full2[i * BLOCK:(i + 1) * BLOCK] = torch.from_numpy(np.frombuffer(out, dtype=np.uint8).copy())
+
+        ldist.decode_and_allgather(full2, per, BLOCK, decode_chunk, n_chunks=2)
+        ok_dec = ok_dec and bool((full2.numpy() == data).all()) and calls == ldist.chunk_ranges(per, 2)
     if rank == 0:
         q.put((all_sizes.tolist(), frame, ok_dec, (lo, hi)))
     else:
