@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Turn gpurun_out/{launches_TAG.csv, prof_TAG.ncu-rep} into the committed summaries under profiles/:
-   profiles/launches_TAG.csv      per-launch gpu__time_duration (ncu --metrics pass, cold cache, serialised)
-   profiles/ncu_TAG_summary.txt   key raw metrics + stall mix + hottest SASS lines of the dominant kernel
-   profiles/traffic.json          dram bytes per launch of the dominant kernel, scaled to the bench batch
-Usage: python profiles/summarize.py TAG [blocks_in_profiled_run] [blocks_in_bench_batch]"""
+   profiles/launches_TAG.csv      per-launch gpu__time_duration (ncu --metrics pass, cold cache, serialised) + shares of the step
+   profiles/ncu_TAG_summary.txt   per profiled kernel: key raw metrics, stall mix, hottest SASS lines
+   profiles/traffic.json          dram bytes per 64 KB block of the scan and the expand kernel (bench.py scales them to its batch)
+Usage: python profiles/summarize.py TAG [blocks_in_profiled_run]"""
 import csv
 import io
 import json
@@ -14,75 +14,97 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 prof_blocks = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
-bench_blocks = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
 out = os.path.join(ROOT, "gpurun_out")
 rep = os.path.join(out, "prof_%s.ncu-rep" % tag)
 
-# ---- launch list ----
-rows = [r for r in csv.reader(l for l in open(os.path.join(out, "launches_%s.csv" % tag)) if not l.startswith("=="))]
-hdr = rows[0]
-ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-with open(os.path.join(ROOT, "profiles", "launches_%s.csv" % tag), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3 (4 GiB batch)\n")
-    f.write("kernel,duration_ns\n")
-    tot = {}
-    for r in rows[1:]:
-        name = r[ki].split("(")[0].replace("<unnamed>::", "")
-        f.write("%s,%s\n" % (name, r[vi]))
-        tot.setdefault(name, []).append(float(r[vi].replace(",", "")))
-    f.write("# share of the decode step (scan + expand_fast + expand_generic), mean per launch:\n")
-    step = sum(sum(v) / len(v) for k, v in tot.items() if k.startswith("lz4_scan") or k.startswith("lz4_expand"))
-    for k, v in tot.items():
-        if k.startswith("lz4_scan") or k.startswith("lz4_expand"):
-            f.write("#   %s: %.1f us  (%.1f %% of the step)\n" % (k, sum(v) / len(v) / 1e3, 100 * sum(v) / len(v) / step))
 
-# ---- raw metrics ----
+def num(x):
+    return float(str(x).replace(",", ""))
+
+
+# ---- launch list ----
+lpath = os.path.join(out, "launches_%s.csv" % tag)
+if os.path.exists(lpath):
+    rows = [r for r in csv.reader(l for l in open(lpath) if not l.startswith("=="))]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    with open(os.path.join(ROOT, "profiles", "launches_%s.csv" % tag), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e (4 GiB batch)\n")
+        f.write("kernel,duration_ns\n")
+        tot = {}
+        for r in rows[1:]:
+            name = r[ki].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+            f.write("%s,%s\n" % (name, r[vi]))
+            tot.setdefault(name, []).append(num(r[vi]))
+        dec = {k: v for k, v in tot.items() if k.startswith("lz4_scan") or k.startswith("lz4_expand")}
+        # the decode launches of the timed steps are the LAST ones of each kind (warm-up and setup come first)
+        step = sum(min(v) for v in dec.values())
+        f.write("# share of the decode step (fastest launch of each kernel; ncu serialises and flushes caches: compare shares, not absolutes):\n")
+        for k, v in dec.items():
+            f.write("#   %s: %.1f us  (%.1f %% of the step), %d launches\n" % (k, min(v) / 1e3, 100 * min(v) / step, len(v)))
+
+# ---- raw metrics, one block per profiled kernel ----
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw)))
-h, v = rr[0], rr[2] if len(rr) > 2 else rr[1]
-m = dict(zip(h, v))
-keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+h = rr[0]
+keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "sm__warps_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
-lines = ["ncu --set full --clock-control none --import-source on -k regex:expand_fast  (bench.py --gib 0.5: %d blocks of 64 KB)" % prof_blocks, ""]
-for k in keys:
-    if k in m:
-        lines.append("%-85s %s" % (k, m[k]))
-lines.append("")
-lines.append("warp stall samples (smsp__pcsamp_warps_issue_stalled_*):")
-for k in sorted(h):
-    if k.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in k:
-        lines.append("  %-30s %s" % (k.replace("smsp__pcsamp_warps_issue_stalled_", ""), m[k]))
-
-# units: dram bytes are reported in MB by this ncu build for this size
-def num(x):
-    return float(x.replace(",", ""))
-unit_scale = 1e6
-rd, wr = num(m["dram__bytes_read.sum"]) * unit_scale, num(m["dram__bytes_write.sum"]) * unit_scale
-per_block = (rd + wr) / prof_blocks
-traffic = {"expand_dram_bytes_per_launch": int(per_block * bench_blocks), "source": "ncu --set full, tag %s" % tag,
-           "profiled_blocks": prof_blocks, "dram_read_bytes": int(rd), "dram_write_bytes": int(wr),
-           "dram_bytes_per_block": round(per_block, 1)}
-json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
-lines.append("")
-lines.append("dram bytes per 64 KB block: %.0f  (algorithmic C+U for P50 = %.0f)" % (per_block, 6945762471 / 65536))
-
-# ---- hottest SASS lines ----
+lines = ["ncu --set full --clock-control none --import-source on   python bench.py --gib 0.5 --steps 2 --warmup 3 --no-cpu --no-e2e"
+         "  (%d blocks of 64 KB per launch; one launch per kernel)" % prof_blocks, ""]
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-sr = list(csv.reader(io.StringIO(src)))
-sh = sr[1]
-i_src, i_smp, i_ex = sh.index("Source"), sh.index("# Samples"), sh.index("Instructions Executed")
-data = [(int(r[i_smp]), int(r[i_ex]), r[i_src].strip()) for r in sr[2:] if len(r) > i_ex]
-lines.append("")
-lines.append("SASS: %d instructions in the kernel, %.0f M warp-instructions executed, %d stall samples" %
-             (len(data), sum(d[1] for d in data) / 1e6, sum(d[0] for d in data)))
-lines.append("hottest SASS lines (samples, executions, instruction):")
-for smp, ex, s in sorted(data, reverse=True)[:25]:
-    lines.append("  %7d %11d  %s" % (smp, ex, s[:100]))
-tma = [d for d in data if "UBLKCP" in d[2] or "UTMA" in d[2] or "SYNCS" in d[2]]
-lines.append("")
-lines.append("TMA / mbarrier instructions present in SASS: " + ", ".join(sorted(set(d[2].split()[0] if not d[2].startswith("@") else d[2].split()[1] for d in tma))))
+# the source page concatenates one table per launch, each introduced by a "Kernel Name" line
+tables, cur = [], None
+for row in csv.reader(io.StringIO(src)):
+    if row and row[0] == "Kernel Name":
+        cur = {"name": row[1], "rows": []}
+        tables.append(cur)
+    elif cur is not None:
+        cur["rows"].append(row)
+traffic = {"source": "ncu --set full, tag %s, %d blocks of 64 KB (datagen P50) per launch" % (tag, prof_blocks),
+           "proba": 0.5, "block_bytes": 65536}
+seen = set()
+for idx, v in enumerate(rr[2:]):
+    m = dict(zip(h, v))
+    name = m["Kernel Name"].replace("<unnamed>::", "").replace("void ", "")
+    short = name.split("(")[0].split("<")[0]
+    if short in seen:
+        continue
+    seen.add(short)
+    lines.append("=" * 100)
+    lines.append("kernel: " + name)
+    for k in keys:
+        if k in m:
+            lines.append("  %-85s %s" % (k, m[k]))
+    rd, wr = num(m["dram__bytes_read.sum"]) * 1e6, num(m["dram__bytes_write.sum"]) * 1e6      # this ncu build reports MB here
+    per_block = (rd + wr) / prof_blocks
+    lines.append("  dram bytes per 64 KB block: %.0f   (algorithmic C+U for P50 = %.0f)" % (per_block, 6945762471 / 65536))
+    lines.append("  warp-instructions per 64 KB block: %.0f" % (num(m["smsp__inst_executed.sum"]) / prof_blocks))
+    if "expand" in short:
+        traffic["expand_dram_bytes_per_block"] = round(per_block, 1)
+    elif "scan" in short:
+        traffic["scan_dram_bytes_per_block"] = round(per_block, 1)
+    lines.append("  stalls per issued instruction (smsp__average_warps_issue_stalled_*_per_issue_active):")
+    for k in sorted(h):
+        if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio") and num(m[k]) >= 0.2:
+            lines.append("    %-24s %.2f" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), num(m[k])))
+    tb = next((t for t in tables if t["name"].replace("<unnamed>::", "").replace("void ", "") == name), None)
+    if tb and len(tb["rows"]) > 2:
+        sh = tb["rows"][0]
+        i_src, i_smp, i_ex = sh.index("Source"), sh.index("# Samples"), sh.index("Instructions Executed")
+        data = [(int(r[i_smp]), int(r[i_ex]), r[i_src].strip()) for r in tb["rows"][1:] if len(r) > i_ex]
+        lines.append("  SASS: %d instructions, %.0f M warp-instructions executed, %d stall samples" %
+                     (len(data), sum(d[1] for d in data) / 1e6, sum(d[0] for d in data)))
+        lines.append("  hottest SASS lines (samples, executions, instruction):")
+        for smp, ex, s in sorted(data, reverse=True)[:16]:
+            lines.append("    %7d %11d  %s" % (smp, ex, s[:96]))
+        tma = [d for d in data if any(t in d[2] for t in ("UBLKCP", "UTMA", "SYNCS", "LDGSTS"))]
+        mn = sorted(set(d[2].split()[0] if not d[2].startswith("@") else d[2].split()[1] for d in tma))
+        lines.append("  TMA / mbarrier / cp.async instructions in the SASS: " + (", ".join(mn) if mn else "-"))
+    lines.append("")
+json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", "ncu_%s_summary.txt" % tag), "w").write("\n".join(lines) + "\n")
-print("\n".join(lines[:45]))
+print("\n".join(lines[:70]))
