@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--proba", type=float, default=0.5, help="datagen match probability (P50)")
     ap.add_argument("--accel", type=int, default=1)
     ap.add_argument("--block-kb", type=int, default=64, help="block size in KB (64 = BASELINE configs 1-3; 4096 = lz4frame 4 MB blocks)")
+    ap.add_argument("--ref-gib", type=float, default=1.0, help="--impl reference: GiB of the workload each step decodes (bounded sample)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -135,7 +136,10 @@ def run_reference(args):
         return 0
     orc, codec, kind = cpu_codec()
     cores = len(os.sched_getaffinity(0)) or os.cpu_count() or 1
-    gib = args.gib if cores >= 32 else min(args.gib, 1.0)
+    # a BOUNDED sample of the workload: the first GiB of the same stream (same generator, seeds, block size).  Measured on
+    # the driver's boxes (profiles/): over 4 GiB the same code runs 2-4x slower and unstable on a shared host, over 1 GiB it
+    # reproduces within a few percent -- and the faster figure is the one a CPU baseline should be given.
+    gib = min(args.gib, args.ref_gib)
     n_blocks = int(gib * (1 << 30)) // BLOCK
     data = np.empty(n_blocks * BLOCK, dtype=np.uint8)
     orc.first_touch(data, BLOCK, n_blocks, cores)
@@ -170,14 +174,14 @@ def run_reference(args):
     med, best, mean = float(np.median(times)), min(times), sum(times) / len(times)
     nbytes = n_blocks * BLOCK
     value = nbytes / med / GB
-    sample = "%d blocks of %d KB (%.2f GiB) datagen P%d, %d pinned host threads (one per CPU), static partition, packed input" % (
+    sample = "the first %d blocks of %d KB (%.2f GiB) of the workload, datagen P%d, %d pinned host threads (one per CPU), static partition, packed input" % (
         n_blocks, BLOCK // 1024, nbytes / (1 << 30), round(args.proba * 100), cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": round(1e3 * med, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(n_blocks, gib, args.proba, args.accel, nbytes / float(csz.sum()), args.gpus),
+        "config": workload_config(int(args.gib * (1 << 30)) // BLOCK, args.gib, args.proba, args.accel, nbytes / float(csz.sum()), args.gpus),
         "timing": {"value_from": "median step", "best_GBps": round(nbytes / best / GB, 3),
                    "median_GBps": round(value, 3), "mean_GBps": round(nbytes / mean / GB, 3),
                    "spread": round(max(times) / best, 3)},
@@ -303,6 +307,27 @@ def run_ours(args):
     tc1 = time.time()
     compress_ms = ev0.elapsed_time(ev1) / KC
     compress_clocks = sampler.summary(tc0, tc1)
+    # the parallel-parse compressor (throughput mode): valid LZ4, deterministic, not byte-identical; same clocks rule
+    pslots = torch.empty_like(slots)
+    psizes = torch.empty_like(csizes)
+    batch.compress_blocks(src, BLOCK, args.accel, slots=pslots, out_sizes=psizes, mode="parallel")
+    torch.cuda.synchronize()
+    tp0 = time.time()
+    ev0.record()
+    for _ in range(KC):
+        batch.compress_blocks(src, BLOCK, args.accel, slots=pslots, out_sizes=psizes, mode="parallel")
+    ev1.record()
+    torch.cuda.synchronize()
+    tp1 = time.time()
+    par_ms = ev0.elapsed_time(ev1) / KC
+    par_clocks = sampler.summary(tp0, tp1)
+    psz_host = psizes.cpu().numpy()
+    par_bytes = int(psz_host.sum())
+    for i in np.random.default_rng(100 + rank).integers(0, n_blocks, 8):     # checker: the ORACLE's decoder expands it to the input
+        blk = pslots[i * stride:i * stride + int(psz_host[i])].cpu().numpy().tobytes()
+        dret, dout = orc.decompress(blk, BLOCK)
+        assert dret == BLOCK and dout == host[i * BLOCK:(i + 1) * BLOCK].tobytes(), "parallel compressor: block %d does not round-trip" % i
+    del pslots
     packed, offs_all = batch.pack_blocks(slots, stride, csizes)
     offs = offs_all[:-1].contiguous()
     torch.cuda.synchronize()
@@ -505,6 +530,13 @@ def run_ours(args):
                      "roofline": {"bound": "hbm", "achieved": round(algo_bytes / (compress_ms * 1e-3) / GB, 2), "peak": peak,
                                   "unit": "GB/s", "frac": round(algo_bytes / (compress_ms * 1e-3) / GB / peak, 4)},
                      "clocks": compress_clocks},
+        "compress_parallel": {"GBps": round(total / (par_ms * 1e-3) / GB, 3), "ms": round(par_ms, 3),
+                              "ratio": round(total / par_bytes, 4), "ratio_vs_reference": round(comp_bytes / par_bytes, 4),
+                              "accel": args.accel, "steps": KC,
+                              "kernel": "lz4_encode_par_kernel (valid LZ4, deterministic, NOT byte-identical; sample decoded by the oracle)",
+                              "roofline": {"bound": "hbm", "achieved": round((total + par_bytes) / (par_ms * 1e-3) / GB, 2), "peak": peak,
+                                           "unit": "GB/s", "frac": round((total + par_bytes) / (par_ms * 1e-3) / GB / peak, 4)},
+                              "clocks": par_clocks},
     }
     if world > 1:
         line["multi_gpu"] = {"value_includes": "decode + exchange of the decoded shards (grouped NCCL send/recv per chunk, "

@@ -146,6 +146,19 @@ LZ4B200_API int LZ4B200_compress_blocks(const void* d_src, int64_t srcStride, co
                                         int32_t* d_outSize, int64_t nBlocks, void* stream);
 
 /*
+ * The same call with the PARALLEL PARSE (throughput mode): every block is a valid LZ4 block that
+ * LZ4_decompress_safe expands to the input, the result is deterministic, but it is NOT byte-identical to
+ * LZ4_compress_fast: every position is a match candidate (no skipping), matches are chosen by the same greedy
+ * rule, and the compression ratio is within 2 % of the reference's at acceleration 1 (usually above it).
+ * acceleration 1..4 probe every position, 5..12 every 2nd, 13..20 every 3rd, ... (faster, lower ratio -- monotone
+ * like the reference's parameter, not the same curve).  Blocks above 65 536 bytes are compressed by the
+ * byte-identical encoder.  d_outSize[i] == 0: block i did not fit dstCap (as LZ4_compress_fast).
+ */
+LZ4B200_API int LZ4B200_compress_blocks_parallel(const void* d_src, int64_t srcStride, const int32_t* d_srcSize, int32_t srcSize,
+                                        void* d_dst, int64_t dstStride, int32_t dstCap, int acceleration,
+                                        int32_t* d_outSize, int64_t nBlocks, void* stream);
+
+/*
  * Pack per-block slots into one contiguous stream (what the CPU does implicitly by writing blocks
  * back to back, lz4frame.c:1046-1055): d_outOff[i] = sum_{k<i} max(d_sizes[k],0) + i*headerBytes,
  * d_outOff[nBlocks] = total; block i's bytes are copied to d_packed + d_outOff[i] + headerBytes.

@@ -67,8 +67,11 @@ def decompress_blocks(comp, offsets, sizes, block_capacity, out=None, out_stride
 
 
 def compress_blocks(src, block_size, acceleration=1, slots=None, slot_stride=None, slot_capacity=None,
-                    out_sizes=None, src_sizes=None, stream=None):
+                    out_sizes=None, src_sizes=None, stream=None, mode="exact"):
     """Compress src (u8 device tensor) as ceil(len/block_size) independent blocks.
+
+    mode "exact": byte-identical to LZ4_compress_fast (LZ4B200_compress_blocks); mode "parallel": the
+    parallel-parse encoder (LZ4B200_compress_blocks_parallel: valid, deterministic, ratio within 2 %, much faster).
 
     Returns (slots, out_sizes, slot_stride): block i's bytes are slots[i*slot_stride : i*slot_stride+out_sizes[i]].
     """
@@ -87,9 +90,11 @@ def compress_blocks(src, block_size, acceleration=1, slots=None, slot_stride=Non
         if src_sizes is None and n and total != n * block_size:
             src_sizes = torch.full((n,), block_size, dtype=torch.int32, device=src.device)
             src_sizes[-1] = total - (n - 1) * block_size
-    rc = lib.LZ4B200_compress_blocks(src.data_ptr(), int(block_size), src_sizes.data_ptr() if src_sizes is not None else None,
-                                     int(block_size), slots.data_ptr(), stride, cap, int(acceleration),
-                                     out_sizes.data_ptr(), n, st.cuda_stream)
+    if mode not in ("exact", "parallel"):
+        raise ValueError("mode must be 'exact' or 'parallel'")
+    fn = lib.LZ4B200_compress_blocks if mode == "exact" else lib.LZ4B200_compress_blocks_parallel
+    rc = fn(src.data_ptr(), int(block_size), src_sizes.data_ptr() if src_sizes is not None else None,
+            int(block_size), slots.data_ptr(), stride, cap, int(acceleration), out_sizes.data_ptr(), n, st.cuda_stream)
     _lib.check(rc, "LZ4B200_compress_blocks")
     return slots, out_sizes[:n], stride
 

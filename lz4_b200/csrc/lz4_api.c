@@ -51,7 +51,7 @@ int LZ4B200_device_count(void)
     return n;
 }
 
-#define N_PIPE 3   /* chunks in flight for the host-buffer batch calls */
+#define N_PIPE 4   /* chunks in flight for the host-buffer batch calls */
 
 typedef struct {
     int ready;
@@ -174,6 +174,23 @@ int LZ4B200_compress_blocks(const void* d_src, int64_t srcStride, const int32_t*
     return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "lz4k_launch_encode");
 }
 
+int LZ4B200_compress_blocks_parallel(const void* d_src, int64_t srcStride, const int32_t* d_srcSize, int32_t srcSize,
+                                     void* d_dst, int64_t dstStride, int32_t dstCap, int acceleration,
+                                     int32_t* d_outSize, int64_t nBlocks, void* stream)
+{
+    lz4k_encode_args a;
+    cudaError_t e;
+    if (nBlocks < 0) return LZ4B200_ERR_ARG;
+    if (nBlocks == 0) return LZ4B200_OK;
+    if (!d_dst || !d_outSize) return LZ4B200_ERR_ARG;
+    a.src = (const uint8_t*)d_src; a.srcStride = srcStride; a.srcSizeArr = d_srcSize; a.srcSize = srcSize;
+    a.dst = (uint8_t*)d_dst; a.dstStride = dstStride; a.dstCap = dstCap; a.acceleration = acceleration;
+    a.outSize = d_outSize; a.nBlocks = nBlocks;
+    /* the parallel parse stages a whole block in shared memory: blocks above 64 KB take the byte-identical encoder */
+    e = (cudaError_t)(srcSize <= 65536 ? lz4k_launch_encode_par(&a, stream) : lz4k_launch_encode(&a, stream));
+    return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "lz4k_launch_encode_par");
+}
+
 int LZ4B200_pack_blocks(const void* d_slots, int64_t slotStride, const int32_t* d_sizes, int64_t nBlocks,
                         void* d_packed, int64_t* d_outOff, int headerBytes, void* stream)
 {
@@ -188,7 +205,20 @@ int LZ4B200_pack_blocks(const void* d_slots, int64_t slotStride, const int32_t* 
 /* ------------------------------------------------------------------------------------------ */
 /* host-buffer batch calls: H2D -> kernels -> D2H, N_PIPE chunks in flight                     */
 /* ------------------------------------------------------------------------------------------ */
-#define CHUNK_OUT_BYTES ((int64_t)256 << 20)   /* target decoded bytes per pipeline chunk */
+/* target uncompressed bytes per pipeline chunk: large enough that a chunk's kernels run at batch speed, small enough that
+ * the first H2D and the last D2H (which nothing overlaps) are a small part of the call.  LZ4B200_HOST_CHUNK_MB overrides
+ * it (developer knob for tests/perf). */
+static int64_t chunk_out_bytes(void)
+{
+    static int64_t v = 0;
+    if (v == 0) {
+        const char* e = getenv("LZ4B200_HOST_CHUNK_MB");
+        long mb = e ? atol(e) : 0;
+        v = (int64_t)((mb >= 1 && mb <= 4096) ? mb : 128) << 20;
+    }
+    return v;
+}
+#define CHUNK_OUT_BYTES chunk_out_bytes()
 
 int LZ4B200_decompress_blocks_host(const void* h_src, const int64_t* h_srcOff, const int32_t* h_srcSize,
                                    void* h_dst, int64_t dstStride, int32_t dstCap,
@@ -564,7 +594,7 @@ int64_t LZ4B200_decompressFrame_host(const void* h_src, int64_t srcSize, void* h
     int64_t* off = NULL; int32_t* csz = NULL; int32_t* rets = NULL; uint8_t* raw = NULL;
     int64_t result = LZ4B200_ERR_FRAME;
     uint32_t flg, bd, hdrLen;
-    int bsid, needCompact = 0;
+    int bsid;
     if (!h_src || srcSize < 0 || dstCapacity < 0 || (!h_dst && dstCapacity > 0)) return LZ4B200_ERR_ARG;
     if (srcSize < 7) return LZ4B200_ERR_FRAME;                            /* minFHSize, lz4frame.h:280 */
     if ((rd_le32(src) & 0xFFFFFFF0u) == FRAME_MAGIC_SKIPPABLE) return LZ4B200_ERR_UNSUPPORTED;
@@ -592,11 +622,15 @@ int64_t LZ4B200_decompressFrame_host(const void* h_src, int64_t srcSize, void* h
         sz = (int64_t)(h & 0x7FFFFFFFu);
         if (sz > bs || ip + sz > srcSize) goto done;                       /* lz4frame.c:1745: maxBlockSize_invalid */
         if (nBlocks == capBlocks) {
+            int64_t* o2; int32_t* c2; uint8_t* r2;
             capBlocks = capBlocks ? capBlocks * 2 : 1024;
-            off = (int64_t*)realloc(off, (size_t)capBlocks * sizeof(int64_t));
-            csz = (int32_t*)realloc(csz, (size_t)capBlocks * sizeof(int32_t));
-            raw = (uint8_t*)realloc(raw, (size_t)capBlocks);
-            if (!off || !csz || !raw) { result = LZ4B200_ERR_ARG; goto done; }
+            o2 = (int64_t*)realloc(off, (size_t)capBlocks * sizeof(int64_t));
+            if (o2) off = o2;
+            c2 = (int32_t*)realloc(csz, (size_t)capBlocks * sizeof(int32_t));
+            if (c2) csz = c2;
+            r2 = (uint8_t*)realloc(raw, (size_t)capBlocks);
+            if (r2) raw = r2;
+            if (!o2 || !c2 || !r2) { result = LZ4B200_ERR_ARG; goto done; }     /* (the old blocks are freed at `done`) */
         }
         off[nBlocks] = ip; csz[nBlocks] = (int32_t)sz; raw[nBlocks] = (uint8_t)(h >> 31);
         nBlocks++;
@@ -605,63 +639,53 @@ int64_t LZ4B200_decompressFrame_host(const void* h_src, int64_t srcSize, void* h
     if (consumed) *consumed = ip;
     if (nBlocks == 0) { result = (contentSize > 0) ? LZ4B200_ERR_FRAME : 0; goto done; }
 
-    /* Blocks of a one-shot frame are all full except the last, so block i lands at i * blockSize; every
-     * block is decoded with dstCapacity = maxBlockSize like lz4frame.c:1901-1904 does.  All blocks but the
-     * last go straight into h_dst; the last one (and anything irregular) through a bounce buffer. */
+    if (contentSize >= 0 && contentSize > dstCapacity) { result = LZ4B200_ERR_DSTSIZE; goto done; }
+    /* Every block is decoded with dstCapacity = maxBlockSize like lz4frame.c:1901-1904 does.  The frame is untrusted
+     * input, so memory is bounded whatever it claims: blocks are decoded in GROUPS of at most ~256 MiB of block slots,
+     * straight into h_dst while a group's slots (count x maxBlockSize) fit behind the bytes written so far -- short
+     * blocks are then closed up in place -- and through one reusable bounce buffer otherwise (the tail of the caller's
+     * buffer, or a flushed stream of many short blocks); the running total is checked after every group. */
     rets = (int32_t*)malloc((size_t)nBlocks * sizeof(int32_t));
     if (!rets) { result = LZ4B200_ERR_ARG; goto done; }
     {
-        const int64_t direct = nBlocks - 1;
-        /* regular frames decode straight into h_dst; a frame with short non-final blocks (a flushed
-         * stream) may need more room than the caller's buffer while its blocks sit at i * blockSize */
-        const int useTemp = (direct * bs > dstCapacity);
-        uint8_t* base = dst;
+        int64_t G = ((int64_t)256 << 20) / bs, g0;
         uint8_t* bounce = NULL;
-        uint8_t* temp = NULL;
-        int64_t w = 0;
-        if (useTemp) {
-            temp = (uint8_t*)malloc((size_t)(direct * bs));
-            if (!temp) { result = LZ4B200_ERR_ARG; goto done; }
-            base = temp;
-        }
-        if (direct > 0) {
+        int32_t* tmpSz = NULL;
+        if (G < 1) G = 1;
+        if (G > nBlocks) G = nBlocks;
+        tmpSz = (int32_t*)malloc((size_t)G * sizeof(int32_t));
+        if (!tmpSz) { result = LZ4B200_ERR_ARG; goto done; }
+        for (g0 = 0; g0 < nBlocks; g0 += G) {
+            const int64_t cnt = (nBlocks - g0 < G) ? nBlocks - g0 : G;
+            const int direct = (total + cnt * bs <= dstCapacity);
+            uint8_t* base;
+            int64_t pos = total;
+            int anyGpu = 0, rc = LZ4B200_OK;
+            if (!direct && !bounce) {
+                bounce = (uint8_t*)malloc((size_t)(G * bs));
+                if (!bounce) { free(tmpSz); result = LZ4B200_ERR_ARG; goto done; }
+            }
+            base = direct ? dst + total : bounce;
             /* stored-raw blocks need no GPU: they enter the batch with size 0 (rejected there) and are copied here */
-            int32_t* tmpSz = (int32_t*)malloc((size_t)direct * sizeof(int32_t));
-            int rc;
-            if (!tmpSz) { free(temp); result = LZ4B200_ERR_ARG; goto done; }
-            for (k = 0; k < direct; k++) tmpSz[k] = raw[k] ? 0 : csz[k];
-            rc = LZ4B200_decompress_blocks_host(src, off, tmpSz, base, bs, (int32_t)bs, rets, direct);
-            free(tmpSz);
-            if (rc != LZ4B200_OK) { free(temp); result = rc; goto done; }
-            for (k = 0; k < direct; k++) {
-                if (raw[k]) { memcpy(base + k * bs, src + off[k], (size_t)csz[k]); rets[k] = csz[k]; }
-                if (rets[k] < 0) { free(temp); goto done; }               /* a block failed to decode */
-                if (rets[k] != bs) needCompact = 1;
+            for (k = 0; k < cnt; k++) { tmpSz[k] = raw[g0 + k] ? 0 : csz[g0 + k]; anyGpu |= !raw[g0 + k]; }
+            if (anyGpu) rc = LZ4B200_decompress_blocks_host(src, off + g0, tmpSz, base, bs, (int32_t)bs, rets + g0, cnt);
+            if (rc != LZ4B200_OK) { free(bounce); free(tmpSz); result = rc; goto done; }
+            for (k = 0; k < cnt; k++) {
+                int64_t r;
+                if (raw[g0 + k]) { memcpy(base + k * bs, src + off[g0 + k], (size_t)csz[g0 + k]); rets[g0 + k] = csz[g0 + k]; }
+                r = rets[g0 + k];
+                if (r < 0) { free(bounce); free(tmpSz); goto done; }      /* a block failed to decode */
+                if (pos + r > dstCapacity || (contentSize >= 0 && pos + r > contentSize)) {
+                    free(bounce); free(tmpSz);
+                    result = (pos + r > dstCapacity) ? LZ4B200_ERR_DSTSIZE : LZ4B200_ERR_FRAME;
+                    goto done;
+                }
+                if (dst + pos != base + k * bs) memmove(dst + pos, base + k * bs, (size_t)r);      /* close the gap (moves left) */
+                pos += r;
             }
+            total = pos;
         }
-        bounce = (uint8_t*)malloc((size_t)bs);
-        if (!bounce) { free(temp); result = LZ4B200_ERR_ARG; goto done; }
-        k = nBlocks - 1;
-        if (raw[k]) { memcpy(bounce, src + off[k], (size_t)csz[k]); rets[k] = csz[k]; }
-        else {
-            int rc = LZ4B200_decompress_blocks_host(src, off + k, csz + k, bounce, bs, (int32_t)bs, rets + k, 1);
-            if (rc != LZ4B200_OK) { free(bounce); free(temp); result = rc; goto done; }
-            if (rets[k] < 0) { free(bounce); free(temp); goto done; }
-        }
-        if (needCompact || useTemp) {                                     /* close the gaps / move out of the temp buffer */
-            for (k = 0; k < direct; k++) {
-                if (w + rets[k] > dstCapacity) { free(bounce); free(temp); result = LZ4B200_ERR_DSTSIZE; goto done; }
-                if (base + k * bs != dst + w) memmove(dst + w, base + k * bs, (size_t)rets[k]);
-                w += rets[k];
-            }
-            total = w;
-        } else {
-            total = direct * bs;
-        }
-        if (total + rets[nBlocks - 1] > dstCapacity) { free(bounce); free(temp); result = LZ4B200_ERR_DSTSIZE; goto done; }
-        memcpy(dst + total, bounce, (size_t)rets[nBlocks - 1]);
-        total += rets[nBlocks - 1];
-        free(bounce); free(temp);
+        free(bounce); free(tmpSz);
     }
     if (contentSize >= 0 && contentSize != total) goto done;              /* lz4frame.c: frameSize_wrong */
     result = total;

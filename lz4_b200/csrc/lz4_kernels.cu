@@ -888,6 +888,8 @@ __global__ void __launch_bounds__(32) lz4_encode_kernel(lz4k_encode_args a)
     }
 }
 
+#include "lz4_encode_par.cuh"
+
 /* =============================================================================================
  * pack: exclusive scan of sizes (+ optional 4-byte headers) and gather into a contiguous stream
  * ============================================================================================= */
@@ -1054,6 +1056,25 @@ int lz4k_launch_encode(const lz4k_encode_args* a, void* stream)
     int64_t grid = (int64_t)sms * perSm;
     if (grid > a->nBlocks) grid = a->nBlocks;
     lz4_encode_kernel<<<(unsigned)grid, 32, kEncodeTableBytes, s>>>(*a);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int lz4k_launch_encode_par(const lz4k_encode_args* a, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->nBlocks == 0) return 0;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaFuncSetAttribute(lz4_encode_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncParSmem));
+        if (e != cudaSuccess) return (int)e;
+        sms = v;
+    }
+    const int64_t grid = a->nBlocks < sms ? a->nBlocks : sms;        // persistent: one CTA per SM, blocks c, c + grid, ...
+    lz4_encode_par_kernel<<<(unsigned)grid, kEpThreads, sizeof(EncParSmem), s>>>(*a);
     g_launches++;
     return (int)cudaGetLastError();
 }

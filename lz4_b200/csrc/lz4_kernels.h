@@ -46,7 +46,8 @@ size_t lz4k_decode_workspace_bytes(int64_t nBlocks);   /* any capacities */
 size_t lz4k_decode_workspace_bytes_for(int64_t nBlocks, int perBlockCaps, int32_t dstCap);
 /* phases: bit 0 = scan (validate, sizes), bit 1 = expand (move bytes; needs a prior scan's outSize) */
 int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream);
-int lz4k_launch_encode(const lz4k_encode_args* a, void* stream);
+int lz4k_launch_encode(const lz4k_encode_args* a, void* stream);       /* byte-identical to LZ4_compress_fast */
+int lz4k_launch_encode_par(const lz4k_encode_args* a, void* stream);   /* parallel parse; blocks of <= 65 536 bytes */
 int lz4k_launch_pack(const uint8_t* slots, int64_t slotStride, const int32_t* sizes, int64_t nBlocks,
                      uint8_t* packed, int64_t* outOff, int headerBytes, void* stream);
 uint64_t lz4k_launch_count(void);
