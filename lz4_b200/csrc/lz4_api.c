@@ -214,7 +214,7 @@ static int64_t chunk_out_bytes(void)
     if (v == 0) {
         const char* e = getenv("LZ4B200_HOST_CHUNK_MB");
         long mb = e ? atol(e) : 0;
-        v = (int64_t)((mb >= 1 && mb <= 4096) ? mb : 128) << 20;
+        v = (int64_t)((mb >= 1 && mb <= 4096) ? mb : 64) << 20;
     }
     return v;
 }
@@ -639,7 +639,6 @@ int64_t LZ4B200_decompressFrame_host(const void* h_src, int64_t srcSize, void* h
     if (consumed) *consumed = ip;
     if (nBlocks == 0) { result = (contentSize > 0) ? LZ4B200_ERR_FRAME : 0; goto done; }
 
-    if (contentSize >= 0 && contentSize > dstCapacity) { result = LZ4B200_ERR_DSTSIZE; goto done; }
     /* Every block is decoded with dstCapacity = maxBlockSize like lz4frame.c:1901-1904 does.  The frame is untrusted
      * input, so memory is bounded whatever it claims: blocks are decoded in GROUPS of at most ~256 MiB of block slots,
      * straight into h_dst while a group's slots (count x maxBlockSize) fit behind the bytes written so far -- short

@@ -84,6 +84,9 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
     const int step = accel <= 4 ? 1 : 1 + (accel + 3) / 8;       /* every position for acceleration 1..4, then every 2nd (5..12), 3rd (13..20), ... */
     if (tid == 0) mbar_init(&S.mbar, 1);
     __syncthreads();
+#ifdef LZ4K_PHASE_TIMING
+    long long tPhase = clock64();
+#endif
 
     for (int64_t b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
         const uint8_t* gsrc = a.src + b * a.srcStride;
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 }
             }
             __syncthreads();
+            PHASE_MARK(0);                                     // find 1
             /* ---------------- find, part 2: choose the candidate, enter the table ---------------- */
             uint32_t cnd[4];
             uint32_t hasMask = 0;
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
             }
             if (hasMask) atomicOr(&S.hasBits[i0 >> 5], hasMask << (i0 & 31));
             __syncthreads();
+            PHASE_MARK(1);                                     // find 2
             /* ---------------- lengths: run starts extend, the others point at their run start ---------------- */
             {
                 uint32_t prevC = (i0 > 0) ? S.cand[i0 - 1] : 0xFFFFu;             /* (a window's first position always starts a run) */
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 }
             }
             __syncthreads();
+            PHASE_MARK(2);                                     // lengths
             /* ---------------- long matches: one warp per queued run start, 128 bytes per iteration ---------------- */
             {
                 const uint32_t nJobs = min(S.nJobs, (uint32_t)kEpMaxJobs);
@@ -232,6 +238,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 }
             }
             __syncthreads();
+            PHASE_MARK(3);                                     // long matches
             if (tid == 0) S.nJobs = 0;
             /* ---------------- select: the greedy chain through this window (warp 0, 128 positions per lane) ---------------- */
             if (warp == 0) {
@@ -276,6 +283,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 if (lane == 31) S.E = (uint32_t)exitE;
             }
             __syncthreads();
+            PHASE_MARK(4);                                     // select
             /* ---------------- emit: <= 1 sequence per thread ---------------- */
             {
                 const uint32_t mine = (S.selBits[i0 >> 5] >> (i0 & 31)) & 0xFu;
@@ -324,6 +332,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 }
                 __syncthreads();
                 if (tid == 0) S.nLitJobs = 0;
+                PHASE_MARK(5);                                 // emit
             }
         }
         /* ---------------- last literals (lz4.c:1302-1329) ---------------- */
@@ -345,5 +354,6 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
             if (tid == 0) a.outSize[b] = ok ? (int32_t)total : 0;
         }
         __syncthreads();                                               /* S is reused by the next block */
+        PHASE_MARK(6);                                     // load + tables + last literals
     }
 }

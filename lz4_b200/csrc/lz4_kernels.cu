@@ -619,6 +619,24 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
                 if ((wv + 1) * kWave <= total) rows_resolve<true>(sa, p0, outS + (uint32_t)(wv * kWave), 0xFFFFFFFFu, outS, rowsS, tabS, zeroS, le);
                 else rows_resolve<false>(sa, p0, outS + (uint32_t)(wv * kWave), (uint32_t)total, outS, rowsS, tabS, zeroS, le);
             };
+#ifdef LZ4K_WAVE_BARSYNC
+            /* debug build: the same waves with a plain CTA barrier instead of the split mbarrier (no overlap of the
+             * resolve with the wait).  compute-sanitizer's racecheck does not model mbarrier arrive / wait as
+             * synchronisation; this variant shows that the wave structure itself is hazard free. */
+            for (int wv = 0; wv < nWaves; wv++) {
+                resolve(wv);
+                const uint32_t p0 = (uint32_t)(wv * kWave + tid);
+                const uint32_t lim = ((wv + 1) * kWave <= total) ? 0xFFFFFFFFu : (uint32_t)total;
+                uint32_t v[kRowsRpt];
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++) v[r] = lds_u8(sa[r]);
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++)
+                    if (p0 + (uint32_t)(r * kRowsThreads) < lim) sts_u8(outS + p0 + (uint32_t)(r * kRowsThreads), v[r]);
+                if (wv == nWaves - 1) fence_proxy_async();
+                __syncthreads();
+            }
+#else
             resolve(0);
             for (int wv = 0; wv < nWaves; wv++) {
                 if (wv > 0) { mbar_wait(&S.wbar, wpar); wpar ^= 1; }   /* every warp has copied wave wv-1 */
@@ -637,6 +655,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
             }
             mbar_wait(&S.wbar, wpar);
             wpar ^= 1;
+#endif
             PHASE_MARK(5);                                     // waves
         }
 

@@ -16,6 +16,7 @@
 #if defined(__CUDACC__)
 #define SC_FN __device__ __forceinline__
 #define SC_MFN __device__ __forceinline__     /* member functions */
+#define SC_MFN_COLD __device__ __noinline__     /* rare paths: kept out of the loops */
 #define SC_DEV __device__
 #define SC_LDG(p) __ldg(p)
 #define SC_FUNNEL_R(lo, hi, s) __funnelshift_r((lo), (hi), (s))
@@ -23,6 +24,7 @@
 #else
 #define SC_FN static inline
 #define SC_MFN inline
+#define SC_MFN_COLD inline
 #define SC_DEV static inline
 #define SC_LDG(p) (*(p))
 static inline uint32_t sc_funnel_r_host(uint32_t lo, uint32_t hi, uint32_t s)
@@ -75,6 +77,7 @@ template <bool G> struct MemPtr {
     SC_MFN uint32_t u16(int64_t i) const { return ld16<G>(p + i); }
     SC_MFN uint32_t u32(int64_t i) const { return ld32u<G>(p + i); }
     SC_MFN void ensure(int64_t) const { }
+    SC_MFN void tick(int64_t) const { }
     SC_MFN void prefetch(int64_t i) const { if (G) SC_PREFETCH_L1(p + i); }
     static constexpr bool kPrefetch = G;
 };
@@ -85,7 +88,7 @@ template <bool G> struct MemPtr {
 constexpr int kRingBytes = LZ4K_RING_BYTES;           /* per-thread window, power of two, 4 quarters */
 constexpr int kRingQuarter = kRingBytes / 4;
 constexpr int kRingStride = kRingBytes + 16;         /* rings of neighbouring lanes start in different banks */
-static_assert((kRingBytes & (kRingBytes - 1)) == 0 && kRingQuarter % 16 == 0 && kRingQuarter >= 2 * kMemAhead, "ring geometry");
+static_assert((kRingBytes & (kRingBytes - 1)) == 0 && kRingBytes >= 128, "ring geometry");
 
 /* the asynchronous copy engine of the ring: cp.async on the device; the host build (tests/emul) queues the copies and
  * performs them at the wait, poisoning the destination in between, so that a read before the wait shows up in the tests */
@@ -133,10 +136,12 @@ struct MemRing {
     uint8_t* ring;             /* this thread's kRingBytes of shared memory (16-byte aligned) */
     int head;                  /* block byte i lives at aligned-space position i + head */
     int aEnd;                  /* head + n: first aligned-space position past the block */
-    int base;                  /* the ring covers aligned-space [base, base + kRingBytes); multiple of kRingQuarter */
-    int ready;                 /* everything in [base, ready) has arrived */
-    int sent;                  /* quarters in [ready, sent) are in flight, one cp.async group each */
+    int lo;                    /* the ring holds (or is receiving) aligned-space [lo, sent); multiples of 16 */
+    int sent;
+    int ready;                 /* everything in [lo, ready) has arrived */
+    uint32_t cnt;              /* loop iterations since init: a refill every kRingTick-th (the same iteration in every lane) */
     RingCopier cp;
+    static constexpr int kRingTick = 4, kTickGranules = 6;
 
     SC_MFN void init(const uint8_t* src, int n, uint8_t* ringMem)
     {
@@ -144,42 +149,50 @@ struct MemRing {
         g16 = src - head;
         ring = ringMem;
         aEnd = head + n;
-        base = ready = sent = 0;
-        top_up();
+        lo = sent = ready = 0;
+        cnt = 0;
+        refill(0);
     }
-    /* issue every quarter the ring has room for (16-byte granules that start inside the block only: at most 15 bytes
-     * past the block's end are read, the same padding rule as the bulk loads of the expand kernel) */
-    SC_MFN void top_up()
+    /* one 16-byte granule (only granules that start inside the block: at most 15 bytes past the block's end are read,
+     * the same padding rule as the bulk loads of the expand kernel) */
+    SC_MFN void granule()
     {
-        while (sent < base + kRingBytes && sent < aEnd) {
-            #pragma unroll
-            for (int k = 0; k < kRingQuarter; k += 16)
-                if (sent + k < aEnd) cp.copy16(ring + ((sent + k) & (kRingBytes - 1)), g16 + sent + k);
-            cp.commit();
-            sent += kRingQuarter;
-        }
+        cp.copy16(ring + (sent & (kRingBytes - 1)), g16 + sent);
+        sent += 16;
+    }
+    /* blocking: make [a16, a16 + kRingBytes) (clipped to the block) the ring's content.  Used at the start and for the
+     * rare jump out of the window (a literal run longer than the look-ahead, or the byte-wise replay stepping back). */
+    SC_MFN_COLD void refill(int a16)
+    {
+        cp.wait(0);
+        if (a16 < lo || a16 > sent) lo = sent = a16;           /* nothing useful in the ring: start over at a16 */
+        while (sent < a16 + kRingBytes && sent < aEnd) granule();
+        cp.commit();
+        cp.wait(0);
+        ready = sent;
+        if (lo < sent - kRingBytes) lo = sent - kRingBytes;
+    }
+    /* once per loop iteration of the front loop (every lane of a warp is in the same iteration): every kRingTick-th
+     * iteration tops the ring up -- straight-line, predicated -- commits the copies as one group and waits for every
+     * OLDER group, i.e. a granule is needed two refills (>= kRingTick iterations) after it was requested */
+    SC_MFN void tick(int64_t i)
+    {
+        if ((cnt++ & (uint32_t)(kRingTick - 1)) != 0u) return;
+        const int a16 = ((int)i + head) & ~15;
+        const int before = sent;
+        #pragma unroll
+        for (int k = 0; k < kTickGranules; k++)
+            if (sent + 16 <= a16 + kRingBytes && sent < aEnd) granule();
+        cp.commit();
+        cp.wait(1);                                            /* all groups but the newest have arrived */
+        if (ready < before) ready = before;
+        if (lo < sent - kRingBytes) lo = sent - kRingBytes;
     }
     SC_MFN void ensure(int64_t i)
     {
         const int a = (int)i + head;
-        const int q = a & ~(kRingQuarter - 1);
-        if (q != base) {
-            if (q > base && q < sent) {                       /* the walk moved on: free the quarters behind it */
-                base = q;
-                if (ready < base) ready = base;               /* (skipped quarters stay in flight; their groups are waited for in order) */
-            } else {                                          /* a jump out of the window (long literal run, or the byte-wise replay going back) */
-                cp.wait(0);
-                base = ready = sent = q;
-            }
-            top_up();
-        }
         const int need = (a + kMemAhead < aEnd ? a + kMemAhead : aEnd);
-        if (need > ready) {
-            const int upto = (need + kRingQuarter - 1) & ~(kRingQuarter - 1);      /* quarters below `upto` must have arrived */
-            const int later = (sent - upto) / kRingQuarter;                         /* groups issued after them */
-            cp.wait(later > 0 ? later : 0);
-            ready = upto < sent ? upto : sent;
-        }
+        if (a < lo || need > ready) refill(a & ~15);
     }
     SC_MFN uint32_t b(int64_t i) const { return ring[((int)i + head) & (kRingBytes - 1)]; }
     SC_MFN uint32_t u16(int64_t i) const { return b(i) | (b(i + 1) << 8); }
@@ -188,9 +201,9 @@ struct MemRing {
         const int a = (int)i + head;
         const uint32_t* w = reinterpret_cast<const uint32_t*>(ring);
         const uint32_t sh = (uint32_t)(a & 3) * 8;
-        const uint32_t lo = w[(a & (kRingBytes - 1)) >> 2];
-        const uint32_t hi = sh ? w[((a + 4) & (kRingBytes - 1)) >> 2] : 0u;
-        return SC_FUNNEL_R(lo, hi, sh);
+        const uint32_t lo32 = w[(a & (kRingBytes - 1)) >> 2];
+        const uint32_t hi32 = sh ? w[((a + 4) & (kRingBytes - 1)) >> 2] : 0u;
+        return SC_FUNNEL_R(lo32, hi32, sh);
     }
     SC_MFN void prefetch(int64_t) const { }
     static constexpr bool kPrefetch = false;
@@ -259,6 +272,7 @@ template <class M> SC_FN bool scan_front(M& mem, int nIn, int capIn, ScanState& 
             nextEvt = ((fip >> 7) + 1) << 7;
         }
         MARK_VISIT(fip, fop);
+        mem.tick(fip);                                             // (ring: top up every few iterations)
         mem.ensure(fip);                                           // [fip, fip + kMemAhead) is readable: token, short literals, offset
         const uint32_t v = mem.u32(fip);                           // token, then the 3 bytes that follow it
         const int mcode = (int)(v & 15u), lit4 = (int)((v >> 4) & 15u);

@@ -8,8 +8,16 @@ O=gpurun_out/sanitizer_$TAG.txt
 mkdir -p gpurun_out
 T="tests/test_gpu_parity.py::test_decode_noisy_source_vs_oracle tests/test_gpu_parity.py::test_mixed_batch_fast_and_slow_lists tests/test_gpu_parity.py::test_compress_random_vs_oracle tests/test_gpu_parity.py::test_decode_overlap_and_long_runs"
 : > $O
-for tool in memcheck racecheck; do
-  echo "===== compute-sanitizer --tool $tool  (python -m pytest $T)" >> $O
-  SANITIZE_SMALL=1 timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python -m pytest $T -x -q -m gpu 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|Error|hazard|=========" | tail -40 >> $O
-done
+run() {   # run <title> <tool> [env...]
+  echo "===== $1: compute-sanitizer --tool $2  (python -m pytest <4 parity tests> -m gpu)" >> $O
+  shift; tool=$1; shift
+  env "$@" timeout 1500 compute-sanitizer --tool $tool --print-limit 12 python -m pytest $T -x -q -m gpu 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|Error|hazard" | cut -c1-200 | tail -16 >> $O
+}
+run "shipped kernels" memcheck X=1
+run "shipped kernels" racecheck X=1
+# racecheck does not model mbarrier arrive/wait (rows kernel) nor cp.async completion (scan ring) as synchronisation;
+# the same kernels with a CTA barrier between the waves and with the ring switched off must be hazard free:
+if [ -f lz4_b200/build/liblz4_b200_barsync.so ]; then
+  run "debug build: CTA barrier between waves (-DLZ4K_WAVE_BARSYNC), scan without ring" racecheck LZ4_B200_LIBRARY=$PWD/lz4_b200/build/liblz4_b200_barsync.so LZ4K_SCAN_IMPL=thread
+fi
 cat $O
