@@ -36,10 +36,11 @@
 constexpr int kEpThreads = 1024;
 constexpr int kEpWin = 4096;                         /* positions per window = 4 per thread */
 constexpr int kEpHashLog = 13;
-constexpr int kEpSoloLen = 36;                       /* bytes a run start compares alone before queueing the match for a warp */
-constexpr int kEpMaxJobs = 512;
+constexpr int kEpSoloLen = 20;                       /* bytes a run start compares alone before queueing the match for a warp */
+constexpr int kEpMaxJobs = 128;                      /* long matches a window finishes with a warp each: the first ones by position */
 constexpr int kEpInlineLits = 32;                    /* literal runs up to this length are copied by the emitting thread */
 constexpr int kEpMaxLitJobs = 1024;
+constexpr int kEpStage = 24576;                      /* a window's output is assembled here and written out coalesced when it fits */
 
 struct EncParSmem {
     alignas(16) uint8_t src[65536 + 64];             /* staged block (keeps the source's 16-byte phase) */
@@ -52,6 +53,7 @@ struct EncParSmem {
     uint32_t hasBits[kEpWin / 32], selBits[kEpWin / 32];
     uint16_t jobIdx[kEpMaxJobs];
     uint32_t litJob[kEpMaxLitJobs][3];               /* {source position, output offset, length} */
+    alignas(16) uint8_t stage[kEpStage];
     uint32_t warpA[32], warpB[32];
     uint32_t nJobs, nLitJobs, E, O, fail;
     alignas(8) uint64_t mbar;
@@ -115,16 +117,29 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
         for (int w = 0; w < nWin; w++) {
             const int c0 = w * kEpWin, i0 = 4 * tid, p0 = c0 + i0;
             /* ---------------- find, part 1: hash, old candidate, publish "earliest of this window" ---------------- */
-            uint32_t v[4], h[4], old[4];
+            uint32_t v[4], h[4], old[4], near[4];
             bool probe[4];
             {
                 const uint32_t at = (uint32_t)(head + p0);
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(src) + (at >> 2);
                 const bool any = p0 <= mflimit;
+                const uint32_t wm = (any && p0 >= 4) ? wp[-1] : 0u;
                 const uint32_t w0 = any ? wp[0] : 0u, w1 = any ? wp[1] : 0u, w2 = any ? wp[2] : 0u;
                 const uint32_t sh = (at & 3u) * 8u;
+                const uint32_t pre = __funnelshift_r(wm, w0, sh);                 /* bytes p0-4 .. p0-1 */
                 const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
                 v[0] = lo; v[1] = __funnelshift_r(lo, hi, 8); v[2] = __funnelshift_r(lo, hi, 16); v[3] = __funnelshift_r(lo, hi, 24);
+                /* near[k] = smallest d in 1..4 with bytes [p-d, p-d+4) == [p, p+4) (a run of period d: RLE-like data), else 0.
+                 * The hash tables hold ONE position per hash, so inside such a run neighbouring positions would get
+                 * unrelated candidates; taking p-d keeps them on one offset (one run, one long match). */
+                const uint32_t b[7] = {pre, __funnelshift_r(pre, lo, 8), __funnelshift_r(pre, lo, 16), __funnelshift_r(pre, lo, 24), v[0], v[1], v[2]};
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {                                     /* b[4 + k - d] = the 4 bytes at p0 + k - d */
+                    near[k] = 0;
+                    #pragma unroll
+                    for (int d = 4; d >= 1; d--)
+                        if (p0 + k - d >= 0 && b[4 + k - d] == v[k]) near[k] = (uint32_t)d;
+                }
             }
             if (tid < kEpWin / 32) { S.hasBits[tid] = 0; }
             #pragma unroll
@@ -150,7 +165,8 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 if (probe[k]) {
                     const uint32_t e = S.T2[h[k]];
                     const int q = c0 + (0xFFFF - (int)(e & 0xFFFFu));                 /* earliest position of this window with this hash */
-                    if (q < p && ep_ld32(src, (uint32_t)(head + q)) == v[k]) cnd[k] = (uint32_t)q;
+                    if (near[k]) cnd[k] = (uint32_t)p - near[k];
+                    else if (q < p && ep_ld32(src, (uint32_t)(head + q)) == v[k]) cnd[k] = (uint32_t)q;
                     else if (old[k] && ep_ld32(src, (uint32_t)head + old[k] - 1u) == v[k]) cnd[k] = old[k] - 1u;
                     atomicMax(&S.T[h[k]], (uint32_t)p + 1u);
                     if (cnd[k] != 0xFFFFu) hasMask |= 1u << k;
@@ -164,13 +180,16 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
             {
                 uint32_t prevC = (i0 > 0) ? S.cand[i0 - 1] : 0xFFFFu;             /* (a window's first position always starts a run) */
                 uint32_t lastStart = 0;                                           /* window index + 1 of the latest run start in this quad */
+                uint32_t longMask = 0;                                            /* run starts of this quad that are still matching after kEpSoloLen bytes */
                 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int p = p0 + k;
                     const bool has = cnd[k] != 0xFFFFu;
                     const bool isStart = has && !(prevC != 0xFFFFu && cnd[k] == prevC + 1u);
                     if (isStart) {
-                        const int limit = matchlimit - p;                          /* longest match allowed here (>= 7) */
+                        /* longest match allowed here: the format's end-of-block rule, and the end of this window -- the rest of a
+                         * longer match is found again by the next window (3 bytes per split), which bounds the work per window */
+                        const int limit = min(matchlimit - p, c0 + kEpWin - p + kMinMatch);
                         int L = 4;
                         const uint32_t pa = (uint32_t)(head + p), ca = (uint32_t)head + cnd[k];
                         while (L < kEpSoloLen && L < limit) {
@@ -179,23 +198,29 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                             L += 4;
                         }
                         if (L > limit) L = limit;
-                        if (L >= kEpSoloLen && L < limit) {                        /* still matching: a warp finishes it */
-                            const uint32_t j = atomicAdd(&S.nJobs, 1u);
-                            if (j < (uint32_t)kEpMaxJobs) S.jobIdx[j] = (uint16_t)(i0 + k);
-                        }
+                        if (L >= kEpSoloLen && L < limit) longMask |= 1u << k;    /* still matching: a warp finishes it */
                         S.len[i0 + k] = (uint16_t)L;
                         lastStart = (uint32_t)(i0 + k) + 1u;
                     }
                     prevC = cnd[k];
                 }
+                /* the long matches of the window, ranked by position (a scheduling-independent order): the first kEpMaxJobs
+                 * are finished by a warp each, the others keep kEpSoloLen (valid, shorter) */
+                uint32_t nl = (uint32_t)__popc(longMask), inclL = nl;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(kFull, inclL, d); if (lane >= d) inclL += y; }
+                if (lane == 31) S.warpB[warp] = inclL;
                 /* inclusive max-scan of lastStart over the threads: the run start at or before each quad's end */
                 uint32_t m = lastStart;
                 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(kFull, m, d); if (lane >= d) m = max(m, y); }
                 if (lane == 31) S.warpA[warp] = m;
                 __syncthreads();
-                uint32_t before = 0;                                              /* latest run start in earlier warps */
-                for (int q = 0; q < warp; q++) before = max(before, S.warpA[q]);
+                uint32_t before = 0, rankL = inclL - nl;                          /* latest run start / long matches in earlier warps */
+                for (int q = 0; q < warp; q++) { before = max(before, S.warpA[q]); rankL += S.warpB[q]; }
+                for (int k = 0; k < 4; k++)
+                    if ((longMask >> k) & 1u) { if (rankL < (uint32_t)kEpMaxJobs) S.jobIdx[rankL] = (uint16_t)(i0 + k); rankL++; }
+                if (tid == kEpThreads - 1) S.nJobs = rankL;
                 uint32_t prevT = __shfl_up_sync(kFull, m, 1);
                 if (lane == 0) prevT = 0;
                 uint32_t run = max(before, prevT);                                /* latest run start before this quad */
@@ -215,7 +240,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
             {
                 const uint32_t nJobs = min(S.nJobs, (uint32_t)kEpMaxJobs);
                 for (uint32_t j = warp; j < nJobs; j += 32) {
-                    const int idx = S.jobIdx[j], p = c0 + idx, limit = matchlimit - p;
+                    const int idx = S.jobIdx[j], p = c0 + idx, limit = min(matchlimit - p, c0 + kEpWin - p + kMinMatch);
                     const uint32_t pa = (uint32_t)(head + p), ca = (uint32_t)head + S.cand[idx];
                     int L = kEpSoloLen;
                     for (;;) {
@@ -239,7 +264,6 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
             }
             __syncthreads();
             PHASE_MARK(3);                                     // long matches
-            if (tid == 0) S.nJobs = 0;
             /* ---------------- select: the greedy chain through this window (warp 0, 128 positions per lane) ---------------- */
             if (warp == 0) {
                 uint32_t has[4], sel[4];
@@ -267,16 +291,22 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                     exitE = e;
                 };
                 walk(eCur);
+                int finalExit = Ein;
                 for (;;) {
-                    int eNew = __shfl_up_sync(kFull, exitE, 1);
+                    /* exit of lanes 0..j = the end of the last match selected at or before lane j (lanes that select nothing pass
+                     * the chain through): a "last valid value" scan instead of one round per lane */
+                    int val = (firstSel >= 0) ? exitE : -1;
+                    #pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(kFull, val, d); if (lane >= d && val < 0) val = y; }
+                    const int incl = (val < 0) ? Ein : val;
+                    int eNew = __shfl_up_sync(kFull, incl, 1);
                     if (lane == 0) eNew = Ein;
-                    const int sOld = max(eCur - c0, segLo), sNew = max(eNew - c0, segLo);
-                    const int exitOld = exitE;
-                    if (sNew != sOld) walk(eNew);
-                    else if (firstSel < 0) exitE = eNew;                          /* nothing selected here: the chain passes through */
+                    const bool need = max(eNew - c0, segLo) != max(eCur - c0, segLo);      /* the search would start elsewhere */
                     eCur = eNew;
-                    if (!__any_sync(kFull, exitE != exitOld)) break;
+                    if (!__any_sync(kFull, need)) { finalExit = __shfl_sync(kFull, incl, 31); break; }
+                    if (need) walk(eNew);
                 }
+                exitE = finalExit;
                 if (firstSel >= 0) S.litStart[firstSel] = (uint16_t)eCur;          /* its literals start at the true entry */
                 #pragma unroll
                 for (int q = 0; q < 4; q++) S.selBits[4 * lane + q] = sel[q];
@@ -301,13 +331,19 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += y; }
                 if (lane == 31) S.warpB[warp] = incl;
                 __syncthreads();
-                uint32_t base = S.O;
-                for (int q = 0; q < warp; q++) base += S.warpB[q];
+                const uint32_t O0 = S.O;
+                uint32_t base = O0, winTotal = 0;
+                for (int q = 0; q < 32; q++) { const uint32_t x = S.warpB[q]; winTotal += x; if (q < warp) base += x; }
+                /* scattered byte stores to global memory cost one memory transaction each: the window's output is put
+                 * together in shared memory and written out as consecutive bytes (windows whose output does not fit --
+                 * a match after a very long literal run -- are written directly) */
+                const bool staged = winTotal <= (uint32_t)kEpStage;
+                uint8_t* const obase = staged ? S.stage - O0 : dst;             /* output offset o lives at obase + o */
                 if (mine) {
                     int64_t o = (int64_t)base + incl - size;
                     if (o + size > cap) S.fail = 1;
                     else {
-                        uint8_t* d = dst + o;
+                        uint8_t* d = obase + o;
                         const uint32_t ml = (uint32_t)(L - kMinMatch);
                         *d++ = (uint8_t)((min((uint32_t)ll, 15u) << 4) | min(ml, 15u));
                         if (ll >= 15) { uint32_t r = (uint32_t)ll - 15u; while (r >= 255u) { *d++ = 255; r -= 255u; } *d++ = (uint8_t)r; }
@@ -315,7 +351,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                             for (int i = 0; i < ll; i++) d[i] = src[head + A + i];
                         } else {
                             const uint32_t j = atomicAdd(&S.nLitJobs, 1u);         /* (at most 4096/33 such runs end in a window) */
-                            S.litJob[j][0] = (uint32_t)A; S.litJob[j][1] = (uint32_t)(d - dst); S.litJob[j][2] = (uint32_t)ll;
+                            S.litJob[j][0] = (uint32_t)A; S.litJob[j][1] = (uint32_t)(d - obase); S.litJob[j][2] = (uint32_t)ll;
                         }
                         d += ll;
                         const uint32_t off = (uint32_t)p - c;
@@ -324,14 +360,17 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                     }
                 }
                 __syncthreads();
-                if (tid == kEpThreads - 1) S.O = base + incl;
+                if (tid == 0) S.O = O0 + winTotal;
                 const uint32_t nLit = S.nLitJobs;
                 for (uint32_t j = warp; j < nLit; j += 32) {
                     const uint32_t from = S.litJob[j][0], to = S.litJob[j][1], cnt = S.litJob[j][2];
-                    for (uint32_t i = lane; i < cnt; i += 32) dst[to + i] = src[head + from + i];
+                    for (uint32_t i = lane; i < cnt; i += 32) obase[to + i] = src[head + from + i];
                 }
                 __syncthreads();
+                if (staged && !S.fail)                                           /* coalesced: consecutive threads, consecutive bytes */
+                    for (uint32_t i = tid; i < winTotal; i += kEpThreads) dst[O0 + i] = S.stage[i];
                 if (tid == 0) S.nLitJobs = 0;
+                __syncthreads();
                 PHASE_MARK(5);                                 // emit
             }
         }

@@ -147,14 +147,9 @@ __device__ __forceinline__ bool rows_eligible(int n, int cap, uint32_t nseq, uin
     return n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && nseq <= (uint32_t)kMaxSeqFast && nseq <= markStride;
 }
 
-/* ---- scan, one THREAD per block ----
- * RING = true (default): every thread owns a kRingBytes ring in shared memory that cp.async keeps a few quarters
- * ahead of its walk (lz4_scan_core.h: MemRing), so the token chain's dependent reads are shared-memory reads;
- * RING = false: the round-1 kernel, reads through the read-only data cache with L1 prefetch hints. */
-template <bool RING>
+/* ---- scan, one THREAD per block: reads through the read-only data cache with L1 prefetch hints ---- */
 __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
 {
-    extern __shared__ __align__(16) uint8_t ringMem[];
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.nBlocks) return;
     const WsView w = ws_view(a);
@@ -164,16 +159,8 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
     uint32_t ns = 0;
     const bool wantMarks = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && w.markStride > 0);
     uint32_t* marks = wantMarks ? (w.marks + b * w.markStride) : nullptr;
-    int r;
-    if (RING && n > 0) {
-        MemRing mem;
-        mem.init(src, n, ringMem + (size_t)threadIdx.x * kRingStride);
-        r = scan_block(mem, n, cap, &ns, marks, w.markStride);
-        mem.cp.wait(0);                                        /* no copy of this thread is in flight when it exits */
-    } else {
-        MemPtr<true> mem{src};
-        r = scan_block(mem, n, cap, &ns, marks, w.markStride);
-    }
+    MemPtr<true> mem{src};
+    const int r = scan_block(mem, n, cap, &ns, marks, w.markStride);
     a.outSize[b] = r;
     w.nSeq[b] = ns;
     if (r > 0 && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
@@ -1029,8 +1016,8 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         cudaError_t e = cudaFuncSetAttribute(lz4_expand_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(lz4_scan_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanParSmem));
         if (e != cudaSuccess) return (int)e;
-        const char* env = getenv("LZ4K_SCAN_IMPL");               /* developer A/B switch: "thread" (no ring) | "ring" | "par" */
-        scanImpl = env ? (env[0] == 't' ? 0 : env[0] == 'p' ? 1 : 2) : -1;
+        const char* env = getenv("LZ4K_SCAN_IMPL");               /* developer A/B switch: "thread" | "par" */
+        scanImpl = env ? (env[0] == 'p' ? 1 : 0) : -1;
         sms = v;
     }
     if (phases & 1) {
@@ -1038,7 +1025,7 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         if (e != cudaSuccess) return (int)e;
         /* measured (profiles/): the lanes of the parallel scan re-walk their segments several times, ~10x the instructions of the
          * one-thread scan, so it only pays for blocks far beyond 64 KB (lz4frame's 4 MB blocks: 150 000 dependent steps for one thread) */
-        const bool par = (scanImpl == 0 || scanImpl == 2) ? false : scanImpl == 1 ? true : (a->dstCapArr == nullptr && a->dstCap > 65536);
+        const bool par = scanImpl >= 0 ? scanImpl == 1 : (a->dstCapArr == nullptr && a->dstCap > 65536);
         if (par) {
             const int64_t want = (int64_t)sms * 12;                   // 3 resident CTAs per SM, 4 rounds for balance
             const int64_t grid = a->nBlocks < want ? a->nBlocks : want;
@@ -1046,8 +1033,7 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         } else {
             const int threads = 128;
             const int64_t grid = (a->nBlocks + threads - 1) / threads;
-            if (scanImpl == 0) lz4_scan_kernel<false><<<(unsigned)grid, threads, 0, s>>>(*a);
-            else lz4_scan_kernel<true><<<(unsigned)grid, threads, threads * kRingStride, s>>>(*a);
+            lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
         }
         g_launches++;
     }

@@ -46,12 +46,9 @@ constexpr int kMfLimit = 12;
  * How the scan reads the compressed block.  Every read goes through a "memory" object:
  *   MemPtr<true>   the block lies in GLOBAL memory (read-only data cache loads, L1 prefetch hints)
  *   MemPtr<false>  the block is staged in SHARED memory (plain loads through the generic address space)
- *   MemRing        the block lies in global memory and a per-thread RING in shared memory runs ahead of
- *                  the walk (cp.async, 64-byte quarters): the dependent reads of the token chain then cost a
- *                  shared-memory access instead of an L2 / HBM round trip (one thread per block, 32 unrelated
- *                  streams per warp: without the ring nearly every warp-level load waits for a cache miss)
- * b(i) / u16(i) / u32(i) read bytes [i, i+1/2/4) of the block; ensure(i) must have been called with a
- * position <= i such that i + 4 <= position + kMemAhead since the last jump.
+ * b(i) / u16(i) / u32(i) read bytes [i, i+1/2/4) of the block.  ensure(i) / tick(i) announce where the walk is about to
+ * read; they are no-ops for both kinds (they served a per-thread shared-memory ring fed by cp.async, measured in round 2
+ * and dropped: 2.8 - 6.8 ms against 2.6 ms for the plain loads, profiles/README.md).
  * ------------------------------------------------------------------------------------------- */
 constexpr int kMemAhead = 32;              /* bytes that ensure(i) makes readable: [i, i + kMemAhead) */
 
@@ -80,133 +77,6 @@ template <bool G> struct MemPtr {
     SC_MFN void tick(int64_t) const { }
     SC_MFN void prefetch(int64_t i) const { if (G) SC_PREFETCH_L1(p + i); }
     static constexpr bool kPrefetch = G;
-};
-
-#ifndef LZ4K_RING_BYTES
-#define LZ4K_RING_BYTES 256
-#endif
-constexpr int kRingBytes = LZ4K_RING_BYTES;           /* per-thread window, power of two, 4 quarters */
-constexpr int kRingQuarter = kRingBytes / 4;
-constexpr int kRingStride = kRingBytes + 16;         /* rings of neighbouring lanes start in different banks */
-static_assert((kRingBytes & (kRingBytes - 1)) == 0 && kRingBytes >= 128, "ring geometry");
-
-/* the asynchronous copy engine of the ring: cp.async on the device; the host build (tests/emul) queues the copies and
- * performs them at the wait, poisoning the destination in between, so that a read before the wait shows up in the tests */
-#if defined(__CUDACC__)
-struct RingCopier {
-    SC_MFN void copy16(uint8_t* dst, const uint8_t* src) const
-    {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-    }
-    SC_MFN void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
-    SC_MFN void wait(int pendingAllowed) const            /* groups complete in order: allow the newest `pendingAllowed` to stay in flight */
-    {
-        if (pendingAllowed >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-        else if (pendingAllowed == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-};
-#else
-struct RingCopier {
-    struct Job { uint8_t* dst; const uint8_t* src; int group; };
-    mutable Job jobs[64];
-    mutable int nJobs = 0, nextGroup = 0, doneGroups = 0;
-    void copy16(uint8_t* dst, const uint8_t* src) const
-    {
-        for (int k = 0; k < 16; k++) dst[k] = 0xA7;      /* poison until the wait */
-        jobs[nJobs++] = Job{dst, src, nextGroup};
-    }
-    void commit() const { nextGroup++; }
-    void wait(int pendingAllowed) const
-    {
-        const int upTo = nextGroup - pendingAllowed;     /* groups [0, upTo) must be complete */
-        int kept = 0;
-        for (int j = 0; j < nJobs; j++) {
-            if (jobs[j].group < upTo) { for (int k = 0; k < 16; k++) jobs[j].dst[k] = jobs[j].src[k]; }
-            else jobs[kept++] = jobs[j];
-        }
-        nJobs = kept;
-        if (upTo > doneGroups) doneGroups = upTo;
-    }
-};
-#endif
-
-struct MemRing {
-    const uint8_t* g16;        /* 16-byte aligned address at or below the block's first byte */
-    uint8_t* ring;             /* this thread's kRingBytes of shared memory (16-byte aligned) */
-    int head;                  /* block byte i lives at aligned-space position i + head */
-    int aEnd;                  /* head + n: first aligned-space position past the block */
-    int lo;                    /* the ring holds (or is receiving) aligned-space [lo, sent); multiples of 16 */
-    int sent;
-    int ready;                 /* everything in [lo, ready) has arrived */
-    uint32_t cnt;              /* loop iterations since init: a refill every kRingTick-th (the same iteration in every lane) */
-    RingCopier cp;
-    static constexpr int kRingTick = 4, kTickGranules = 6;
-
-    SC_MFN void init(const uint8_t* src, int n, uint8_t* ringMem)
-    {
-        head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
-        g16 = src - head;
-        ring = ringMem;
-        aEnd = head + n;
-        lo = sent = ready = 0;
-        cnt = 0;
-        refill(0);
-    }
-    /* one 16-byte granule (only granules that start inside the block: at most 15 bytes past the block's end are read,
-     * the same padding rule as the bulk loads of the expand kernel) */
-    SC_MFN void granule()
-    {
-        cp.copy16(ring + (sent & (kRingBytes - 1)), g16 + sent);
-        sent += 16;
-    }
-    /* blocking: make [a16, a16 + kRingBytes) (clipped to the block) the ring's content.  Used at the start and for the
-     * rare jump out of the window (a literal run longer than the look-ahead, or the byte-wise replay stepping back). */
-    SC_MFN_COLD void refill(int a16)
-    {
-        cp.wait(0);
-        if (a16 < lo || a16 > sent) lo = sent = a16;           /* nothing useful in the ring: start over at a16 */
-        while (sent < a16 + kRingBytes && sent < aEnd) granule();
-        cp.commit();
-        cp.wait(0);
-        ready = sent;
-        if (lo < sent - kRingBytes) lo = sent - kRingBytes;
-    }
-    /* once per loop iteration of the front loop (every lane of a warp is in the same iteration): every kRingTick-th
-     * iteration tops the ring up -- straight-line, predicated -- commits the copies as one group and waits for every
-     * OLDER group, i.e. a granule is needed two refills (>= kRingTick iterations) after it was requested */
-    SC_MFN void tick(int64_t i)
-    {
-        if ((cnt++ & (uint32_t)(kRingTick - 1)) != 0u) return;
-        const int a16 = ((int)i + head) & ~15;
-        const int before = sent;
-        #pragma unroll
-        for (int k = 0; k < kTickGranules; k++)
-            if (sent + 16 <= a16 + kRingBytes && sent < aEnd) granule();
-        cp.commit();
-        cp.wait(1);                                            /* all groups but the newest have arrived */
-        if (ready < before) ready = before;
-        if (lo < sent - kRingBytes) lo = sent - kRingBytes;
-    }
-    SC_MFN void ensure(int64_t i)
-    {
-        const int a = (int)i + head;
-        const int need = (a + kMemAhead < aEnd ? a + kMemAhead : aEnd);
-        if (a < lo || need > ready) refill(a & ~15);
-    }
-    SC_MFN uint32_t b(int64_t i) const { return ring[((int)i + head) & (kRingBytes - 1)]; }
-    SC_MFN uint32_t u16(int64_t i) const { return b(i) | (b(i + 1) << 8); }
-    SC_MFN uint32_t u32(int64_t i) const
-    {
-        const int a = (int)i + head;
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(ring);
-        const uint32_t sh = (uint32_t)(a & 3) * 8;
-        const uint32_t lo32 = w[(a & (kRingBytes - 1)) >> 2];
-        const uint32_t hi32 = sh ? w[((a + 4) & (kRingBytes - 1)) >> 2] : 0u;
-        return SC_FUNNEL_R(lo32, hi32, sh);
-    }
-    SC_MFN void prefetch(int64_t) const { }
-    static constexpr bool kPrefetch = false;
 };
 
 /* =============================================================================================

@@ -14,19 +14,4 @@ extern "C" int scan_host(const uint8_t* src, int n, int cap, uint32_t* nSeqOut, 
     return scan_block(mem, n, cap, nSeqOut, marks, (uint32_t)kMaxSeqFast);
 }
 
-// the same scan through the per-thread shared-memory ring (MemRing): the host build of the ring queues its
-// asynchronous copies and poisons their destination until the matching wait, so a read that the device could
-// see before the data arrived changes the result here.  waits[0] receives the number of explicit waits.
-extern "C" int scan_host_ring(const uint8_t* src, int n, int cap, uint32_t* nSeqOut, uint32_t* marks)
-{
-    *nSeqOut = 0;
-    if (n <= 0) { MemPtr<true> m0{src}; return scan_block(m0, n, cap, nSeqOut, marks, (uint32_t)kMaxSeqFast); }
-    alignas(16) static uint8_t ring[kRingBytes];
-    for (int k = 0; k < kRingBytes; k++) ring[k] = 0x5C;
-    MemRing mem;
-    mem.init(src, n, ring);
-    const int r = scan_block(mem, n, cap, nSeqOut, marks, (uint32_t)kMaxSeqFast);
-    mem.cp.wait(0);
-    return r;
-}
 extern "C" int scan_host_max_seq(void) { return kMaxSeqFast; }

@@ -17,10 +17,8 @@ from oracle.pyoracle import Oracle, Reference, have_reference
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module", params=["plain", "ring"])
-def scan(request, tmp_path_factory):
-    """plain: reads straight from the block (MemPtr).  ring: the same scan through the per-thread ring of the
-    device's scan kernel (MemRing); its host build delays every asynchronous copy to the matching wait."""
+@pytest.fixture(scope="module")
+def scan(tmp_path_factory):
     gxx = shutil.which("g++")
     if not gxx:
         pytest.skip("g++ not available")
@@ -30,9 +28,7 @@ def scan(request, tmp_path_factory):
     lib = C.CDLL(so)
     lib.scan_host.restype = C.c_int
     lib.scan_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
-    lib.scan_host_ring.restype = C.c_int
-    lib.scan_host_ring.argtypes = lib.scan_host.argtypes
-    entry = lib.scan_host if request.param == "plain" else lib.scan_host_ring
+    entry = lib.scan_host
     max_seq = lib.scan_host_max_seq()
 
     def run(block, cap, shift=0, want_marks=True):
