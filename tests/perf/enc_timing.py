@@ -29,7 +29,7 @@ def main():
     t1.record()
     torch.cuda.synchronize()
     raw.LZ4B200_debug_phase_cycles(buf)
-    names = ["find 1 (hash, T, T2)", "find 2 (candidate, insert)", "lengths + run starts", "long matches", "select", "emit", "load/tables/tail", "-"]
+    names = ["find 1 (T2: earliest of window)", "find 2 (candidate bits)", "last literals", "-", "select (chain rounds)", "emit + insert", "load + tables", "-"]
     tot = sum(buf[:8])
     print("compress ms per launch %.3f, blocks %d, ratio %.4f" % (t0.elapsed_time(t1) / reps, n_blocks, n_blocks * bs / float(sizes.sum())))
     for n, v in zip(names, buf[:8]):
