@@ -41,6 +41,7 @@ constexpr int kEpPer = 16;                           /* positions per thread and
 constexpr int kEpWin = kEpThreads * kEpPer;          /* 16 384 positions per window */
 constexpr int kEpHashLog = 13;
 constexpr int kEpMaxSel = kEpPer / 4;                /* matches are >= 4 long: at most 4 selections per lane */
+constexpr int kEpSolo = 32;                          /* bytes a lane compares alone (> kEpPer: a longer match ends the lane's walk) */
 constexpr int kEpInlineLits = 32;                    /* literal runs up to this length are copied by the emitting thread */
 constexpr int kEpMaxLitJobs = 512;                   /* (at most 16384/33 longer literal runs end in a window) */
 constexpr int kEpStage = 32768;                      /* a window's output is assembled here when it fits */
@@ -202,31 +203,73 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
             uint32_t sCand[kEpMaxSel];
             int cacheP = -1, cacheL = 0;                               /* the last long match this lane extended (walks repeat) */
             uint32_t cacheC = 0;
-            auto walk = [&](int e) {                       /* the chain enters with "end of the last match" = e */
-                nSel = 0;
-                int rel = max(e - p0, 0);
-                #pragma unroll
-                for (int k = 0; k < kEpMaxSel; k++) {
-                    const uint32_t m = rel < kEpPer ? (has >> rel) : 0u;
-                    if (m != 0u) {
-                        rel += __ffs(m) - 1;
-                        const int p = p0 + rel;
-                        uint32_t c; int L;
-                        if (p == cacheP) { c = cacheC; L = cacheL; }
-                        else {
-                            c = ep_candidate(S, src, head, p, c0);
-                            L = ep_extend(src, head, p, c, matchlimit - p);
-                            if (L >= 32) { cacheP = p; cacheC = c; cacheL = L; }
+            /* One walk of every lane that `go`es: the lane's positions from the chain position e.  A match is compared by its lane
+             * alone for kEpSolo bytes; one that is still running then is the lane's LAST selection (it covers the rest of the lane's
+             * 16 positions) and is finished by the whole warp, 128 bytes per step -- a 500-byte match costs 4 steps instead of 120. */
+            auto walk = [&](bool go, int e) {
+                int pendK = -1;
+                if (go) {
+                    nSel = 0;
+                    int rel = max(e - p0, 0);
+                    #pragma unroll
+                    for (int k = 0; k < kEpMaxSel; k++) {
+                        const uint32_t m = rel < kEpPer ? (has >> rel) : 0u;
+                        if (m != 0u) {
+                            rel += __ffs(m) - 1;
+                            const int p = p0 + rel;
+                            uint32_t c; int L;
+                            if (p == cacheP) { c = cacheC; L = cacheL; }
+                            else {
+                                const int limit = matchlimit - p;
+                                c = ep_candidate(S, src, head, p, c0);
+                                L = ep_extend(src, head, p, c, min(limit, kEpSolo));
+                                if (L >= kEpSolo && L < limit) pendK = k;
+                            }
+                            sPos[k] = p; sCand[k] = c; sLen[k] = L; sLit[k] = e;
+                            nSel = k + 1;
+                            e = p + L;
+                            rel = e - p0;
                         }
-                        sPos[k] = p; sCand[k] = c; sLen[k] = L; sLit[k] = e;
-                        nSel = k + 1;
-                        e = p + L;
-                        rel = e - p0;
+                    }
+                    exitE = e;
+                }
+                unsigned pend = __ballot_sync(kFull, pendK >= 0);
+                while (pend) {
+                    const int sl = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    int jp = 0; uint32_t jc = 0;
+                    #pragma unroll
+                    for (int k = 0; k < kEpMaxSel; k++) if (k == pendK) { jp = sPos[k]; jc = sCand[k]; }
+                    jp = __shfl_sync(kFull, jp, sl); jc = __shfl_sync(kFull, jc, sl);
+                    const int limit = matchlimit - jp;
+                    int L = kEpSolo;
+                    for (;;) {
+                        const int o = L + 4 * lane;
+                        const bool stop = o >= limit;                              /* at or past the allowed end: counts as a mismatch at o */
+                        uint32_t x = 0;
+                        if (!stop) x = ep_ld32(src, (uint32_t)(head + jp + o)) ^ ep_ld32(src, (uint32_t)head + jc + (uint32_t)o);
+                        const unsigned mm = __ballot_sync(kFull, stop || x != 0u);
+                        if (mm) {
+                            const int f = __ffs(mm) - 1;
+                            const uint32_t xf = __shfl_sync(kFull, x, f);
+                            const bool sf = __shfl_sync(kFull, (int)stop, f) != 0;
+                            L = L + 4 * f + (sf ? 0 : ((__ffs(xf) - 1) >> 3));
+                            break;
+                        }
+                        L += 128;
+                    }
+                    if (L > limit) L = limit;
+                    if (lane == sl) {
+                        #pragma unroll
+                        for (int k = 0; k < kEpMaxSel; k++) if (k == pendK) { sLen[k] = L; cacheP = sPos[k]; cacheC = sCand[k]; cacheL = L; }
+                        exitE = jp + L;
                     }
                 }
-                exitE = e;
             };
-            walk(eCur);
+            walk(true, eCur);
+#ifdef LZ4K_PHASE_TIMING
+            unsigned statRounds = 0, statWalks = 1;
+#endif
             for (;;) {
                 /* end of the last match selected at or before this lane (lanes that select nothing pass the chain through) */
                 int val = nSel ? exitE : -1;
@@ -244,8 +287,16 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 eCur = eNew;
                 const int anyNeed = __syncthreads_or(need ? 1 : 0);
                 if (!anyNeed) break;
-                if (need) walk(eNew);
+#ifdef LZ4K_PHASE_TIMING
+                statRounds++; statWalks += need ? 1u : 0u;
+#endif
+                walk(need, eNew);
             }
+#ifdef LZ4K_PHASE_TIMING
+            if (tid == 0) atomicAdd(&g_loopStats[0], (unsigned long long)statRounds);
+            atomicAdd(&g_loopStats[1], (unsigned long long)statWalks);
+            if (tid == 0) atomicAdd(&g_loopStats[3], 1ull);
+#endif
             if (nSel) sLit[0] = eCur;                                     /* the first one's literals start at the true entry */
             if (tid == kEpThreads - 1) {                                 /* the chain's position after this window */
                 int last = nSel ? exitE : -1;

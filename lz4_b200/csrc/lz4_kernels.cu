@@ -47,6 +47,7 @@ __device__ unsigned long long g_loopStats[4];    // phase B: warp iterations, la
 #define LZ4_SCAN_CORE_CONSTANTS
 #include "lz4_scan_core.h"
 #include "lz4_scan_par.h"
+#include "lz4_scan_split.h"
 #include "lz4_rows_core.h"
 
 /* low 5 bytes at p (for the 5-byte hash, lz4.c:785-791) */
@@ -116,7 +117,7 @@ __device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_re
 struct WsHeader { uint32_t slowCount, pad[3]; };
 
 struct WsView {
-    WsHeader* hdr; uint32_t* nSeq; uint32_t* slowList; uint32_t* marks; uint32_t markStride;
+    WsHeader* hdr; uint32_t* nSeq; uint32_t* slowList; uint32_t* marks; uint32_t* scratch; uint32_t markStride;
 };
 /* mark slots per block: a block the shared-memory expand kernel may take (capacity <= 64 KB) has at most
  * capacity/4 + 1 sequences (every sequence but the last produces >= 4 bytes) and the scan visits at most one more;
@@ -135,7 +136,8 @@ __host__ __device__ inline WsView ws_view(void* ws, int64_t n, uint32_t markStri
     v.hdr = reinterpret_cast<WsHeader*>(p); p += 256;
     v.nSeq = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
     v.slowList = reinterpret_cast<uint32_t*>(p); p += ((n * 4 + 255) / 256) * 256;
-    v.marks = reinterpret_cast<uint32_t*>(p);
+    v.marks = reinterpret_cast<uint32_t*>(p); p += (((size_t)n * markStride * 4 + 255) / 256) * 256;
+    v.scratch = reinterpret_cast<uint32_t*>(p);                /* split scan: 2 x markStride words per block */
     v.markStride = markStride;
     return v;
 }
@@ -164,6 +166,64 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
     a.outSize[b] = r;
     w.nSeq[b] = ns;
     if (r > 0 && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
+}
+
+/* ---- scan, kSsLanes lanes per block that merge (lz4_scan_split.h): the chain of dependent steps is kSsLanes times shorter ----
+ * The lanes of a block are neighbours in a warp (32 / kSsLanes blocks per warp); phases are separated by __syncwarp.
+ * Lists go to the scratch part of the workspace (2 x markStride words per block), the per-block records to shared memory. */
+constexpr int kSplitThreads = 128;
+constexpr int kSplitBlocksPerCta = kSplitThreads / kSsLanes;
+
+__global__ void __launch_bounds__(kSplitThreads, 10) lz4_scan_split_kernel(lz4k_decode_args a)
+{
+    __shared__ SsBlock sh[kSplitBlocksPerCta];
+    const int lane = threadIdx.x % kSsLanes, slot = threadIdx.x / kSsLanes;
+    const int64_t b = (int64_t)blockIdx.x * kSplitBlocksPerCta + slot;
+    if (b >= a.nBlocks) return;                                 /* (whole groups of kSsLanes lanes leave together) */
+    const unsigned grp = ((1u << kSsLanes) - 1u) << ((threadIdx.x & 31) / kSsLanes * kSsLanes);   /* this block's lanes in the warp */
+    const WsView w = ws_view(a);
+    const uint8_t* src = a.src + a.srcOff[b];
+    const int n = a.srcSize[b];
+    const int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
+    const bool wantMarks = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && w.markStride > 0);
+    uint32_t* marks = wantMarks ? (w.marks + b * w.markStride) : nullptr;
+    SsBlock& S = sh[slot];
+    MemPtr<true> mem{src};
+    int r = 0;
+    uint32_t ns = 0;
+    bool serial = !(wantMarks && cap >= 64 && n >= kSsMinBytes);
+    if (!serial) {
+        const uint32_t R = w.markStride / kSsLanes;
+        uint32_t* sc = w.scratch + b * 2 * (int64_t)w.markStride;
+        uint32_t* A = sc + (size_t)lane * R;
+        uint32_t* B = sc + w.markStride + (size_t)lane * R;
+        ss_p1(lane, S, mem, n, A, B, R);
+        __syncwarp(grp);
+        ss_p2(lane, S, mem, n, A, B, R, [&](int t) { return sc + w.markStride + (size_t)t * R; });
+        __syncwarp(grp);
+        if (lane == 0) ss_p3(S, [&](int t) { return sc + (size_t)t * R; });
+        __syncwarp(grp);
+        serial = S.fallback != 0;
+        if (!serial) {
+            uint32_t e, c, co;
+            ss_p4(lane, S, cap, A, B, marks, w.markStride, e, c, co);
+            #pragma unroll
+            for (int m = 1; m < kSsLanes; m <<= 1) {
+                const uint32_t e2 = __shfl_xor_sync(grp, e, m), c2 = __shfl_xor_sync(grp, c, m), co2 = __shfl_xor_sync(grp, co, m);
+                if (e2 < e) e = e2;
+                if (c2 < c) { c = c2; co = co2; }
+            }
+            if (lane == 0) { S.errIdx = e; S.capIdx = c; S.capOpn = co; }
+            __syncwarp(grp);                                        /* the final marks of every lane are written */
+            if (lane == 0) r = ss_p5(S, mem, n, cap, &ns, marks, w.markStride);
+        }
+    }
+    if (serial && lane == 0) r = scan_block(mem, n, cap, &ns, marks, w.markStride);
+    if (lane == 0) {
+        a.outSize[b] = r;
+        w.nSeq[b] = ns;
+        if (r > 0 && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
+    }
 }
 
 /* ---- scan, one CTA of NL lanes per block (lz4_scan_par.h): same outputs as lz4_scan_kernel ----
@@ -511,12 +571,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
         for (int k = tid; k < 2048; k += kRowsThreads) S.rows[k] = make_uint2(0u, 0u);
         /* this thread's first marks, fetched while the TMA load is in flight */
         const uint32_t* marks = w.marks + d.b * w.markStride;
-        uint32_t mk[kRowsCache], mkn[kRowsCache];
+        uint32_t mk[kRowsCache];
         #pragma unroll
         for (int i = 0; i < kRowsCache; i++) {
             const int k = tid + i * kRowsThreads;
             mk[i] = (k < nseq) ? marks[k] : 0u;
-            mkn[i] = (k + 1 < nseq) ? marks[k + 1] : 0u;
         }
         __syncthreads();                                   /* rows are zero */
         PHASE_MARK(0);                                     // zeroing + marks
@@ -533,14 +592,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
         for (int i = 0; i < kRowsCache; i++) {
             const int k = tid + i * kRowsThreads;
             if (k < nseq) {
-                sq[i] = rw_parse(in, mk[i], mkn[i], k, k + 1 == nseq, total);
+                sq[i] = rw_parse(in, mk[i], k, k + 1 == nseq);
                 if (sq[i].ll > 0) setBit(sq[i].op, 0);
                 if (sq[i].mlen > 0) rw_match_runs(sq[i].m, sq[i].off, sq[i].mlen, zeroDelta0, setBit);
             }
         }
         for (int k = tid + kRowsCache * kRowsThreads; k < nseq; k += kRowsThreads) {
-            const bool last = (k + 1 == nseq);
-            const RwSeq s = rw_parse(in, marks[k], last ? 0u : marks[k + 1], k, last, total);
+            const RwSeq s = rw_parse(in, marks[k], k, k + 1 == nseq);
             if (s.ll > 0) setBit(s.op, 0);
             if (s.mlen > 0) rw_match_runs(s.m, s.off, s.mlen, zeroDelta0, setBit);
         }
@@ -592,8 +650,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
                 if (k < nseq) emit(sq[i]);
             }
             for (int k = tid + kRowsCache * kRowsThreads; k < nseq; k += kRowsThreads) {
-                const bool last = (k + 1 == nseq);
-                emit(rw_parse(in, marks[k], last ? 0u : marks[k + 1], k, last, total));
+                emit(rw_parse(in, marks[k], k, k + 1 == nseq));
             }
             __syncthreads();
             PHASE_MARK(4);                                     // pass 2
@@ -988,7 +1045,8 @@ int lz4k_debug_phase_cycles(unsigned long long* out8)   /* out8: 12 values (8 ph
 static size_t ws_bytes(int64_t nBlocks, uint32_t markStride)
 {
     const size_t lst = (((size_t)nBlocks * 4 + 255) / 256) * 256;
-    return 256 + 2 * lst + (size_t)nBlocks * markStride * sizeof(uint32_t) + 256;
+    const size_t mk = (((size_t)nBlocks * markStride * sizeof(uint32_t) + 255) / 256) * 256;
+    return 256 + 2 * lst + 3 * mk + 256;                      /* header | nSeq | slowList | marks | scratch (2 x marks) */
 }
 
 size_t lz4k_decode_workspace_bytes(int64_t nBlocks)               /* any capacities (worst case: 32 KB of marks per block) */
@@ -1016,8 +1074,8 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         cudaError_t e = cudaFuncSetAttribute(lz4_expand_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(lz4_scan_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanParSmem));
         if (e != cudaSuccess) return (int)e;
-        const char* env = getenv("LZ4K_SCAN_IMPL");               /* developer A/B switch: "thread" | "par" */
-        scanImpl = env ? (env[0] == 'p' ? 1 : 0) : -1;
+        const char* env = getenv("LZ4K_SCAN_IMPL");               /* developer A/B switch: "thread" | "par" | "split" */
+        scanImpl = env ? (env[0] == 'p' ? 1 : env[0] == 's' ? 2 : 0) : -1;
         sms = v;
     }
     if (phases & 1) {
@@ -1026,7 +1084,12 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         /* measured (profiles/): the lanes of the parallel scan re-walk their segments several times, ~10x the instructions of the
          * one-thread scan, so it only pays for blocks far beyond 64 KB (lz4frame's 4 MB blocks: 150 000 dependent steps for one thread) */
         const bool par = scanImpl >= 0 ? scanImpl == 1 : (a->dstCapArr == nullptr && a->dstCap > 65536);
-        if (par) {
+        /* blocks of 16..64 KB: kSsLanes merging lanes per block; smaller blocks have too few sequences to split */
+        const bool split = scanImpl >= 0 ? scanImpl == 2 : (a->dstCapArr == nullptr && a->dstCap >= 16384 && a->dstCap <= 65536);
+        if (split && !par) {
+            const int64_t grid = (a->nBlocks + kSplitBlocksPerCta - 1) / kSplitBlocksPerCta;
+            lz4_scan_split_kernel<<<(unsigned)grid, kSplitThreads, 0, s>>>(*a);
+        } else if (par) {
             const int64_t want = (int64_t)sms * 12;                   // 3 resident CTAs per SM, 4 rounds for balance
             const int64_t grid = a->nBlocks < want ? a->nBlocks : want;
             lz4_scan_par_kernel<<<(unsigned)grid, kScanLanes, sizeof(ScanParSmem), s>>>(*a);

@@ -54,26 +54,28 @@ struct RwSeq {
     int off;       /* match offset */
 };
 
-/* Sequence k from the scan's marks (token position | output position << 16, lz4_scan_core.h): the lane
- * re-reads only its own token -- literal length incl. extension bytes (lz4.c:1978-2014) and the offset;
- * the match length follows from the next sequence's output position. */
-RW_FN RwSeq rw_parse(const uint8_t* in, uint32_t mk, uint32_t mkn, int k, bool last, int total)
+/* Sequence k from the scan's mark (token position | match start << 16, lz4_scan_core.h): the lane re-reads only its
+ * own token -- literal length incl. extension bytes (lz4.c:1978-2014), the offset and the match length; the last
+ * sequence has no match and its mark holds the end of its literals. */
+RW_FN RwSeq rw_parse(const uint8_t* in, uint32_t mk, int k, bool last)
 {
     RwSeq s;
     const int tok = (int)(mk & 0xFFFFu);
-    s.op = (int)(mk >> 16);
-    if (k != 0 && s.op == 0) s.op = 65536;             /* 16-bit wrap: only an empty final sequence starts at 65536 */
-    int nxt = last ? total : (int)(mkn >> 16);
-    if (!last && nxt == 0) nxt = 65536;
+    int m = (int)(mk >> 16);
+    if (k != 0 && m == 0) m = 65536;                   /* 16-bit wrap: only the last sequence of a 64 KB block ends at 65536 */
     const uint32_t t = in[tok];
     int pp = tok + 1;
     int ll = (int)(t >> 4);
     if (ll == 15) { uint32_t x; do { x = in[pp++]; ll += (int)x; } while (x == 255); }
-    s.ll = ll; s.ls = pp; s.m = s.op + ll;
+    s.ll = ll; s.ls = pp; s.m = m; s.op = m - ll;
     s.off = 0; s.mlen = 0;
     if (!last) {
-        s.off = (int)((uint32_t)in[pp + ll] | ((uint32_t)in[pp + ll + 1] << 8));
-        s.mlen = nxt - s.m;
+        pp += ll;
+        s.off = (int)((uint32_t)in[pp] | ((uint32_t)in[pp + 1] << 8));
+        pp += 2;
+        int ml = (int)(t & 15u);
+        if (ml == 15) { uint32_t x; do { x = in[pp++]; ml += (int)x; } while (x == 255); }
+        s.mlen = ml + 4;
     }
     return s;
 }

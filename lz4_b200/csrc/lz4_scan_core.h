@@ -100,15 +100,17 @@ template <class M> SC_FN bool read_runlength(M& mem, int64_t& ip, int64_t ilimit
     return true;
 }
 
-/* Mark = (token position | output position << 16) of one sequence, written by the scan for every
- * sequence of a block that may go to the shared-memory expand kernel.  With the marks the expand
- * kernel rebuilds all sequence records of a block in parallel (one lane per sequence) instead of
- * re-walking the token chain. */
+/* Mark = (token position | output position of the sequence's MATCH << 16) of one sequence (for the last sequence,
+ * which has no match: the end of its literals = the decoded size), written by the scan for every committed
+ * sequence of a block that may go to the shared-memory expand kernel.  With the marks the expand kernel rebuilds
+ * all sequence records of a block in parallel (one lane per sequence re-reads only its own token: literal
+ * length, offset, match length) instead of re-walking the token chain.  16-bit fields: a value of 65 536 wraps
+ * to 0, which only the last sequence of a 64 KB block can have. */
 constexpr int kMaxSeqFast = 8192;              // most sequences a block of the shared-memory expand kernel may have
 /* `markCap` = number of mark slots the caller reserved for this block (<= kMaxSeqFast); a block that can be
  * expanded from shared memory has at most capacity/4 + 1 sequences (every sequence but the last makes >= 4 bytes) */
-#define MARK_VISIT(tokpos, outpos)                                                              \
-    do { if (marks && nseq < markCap) marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(outpos) << 16); } while (0)
+#define MARK_COMMIT(tokpos, matchpos)                                                           \
+    do { if (marks && nseq < markCap) marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(matchpos) << 16); } while (0)
 
 /* where the walk of one block stands between its two loops */
 struct ScanState {
@@ -141,8 +143,7 @@ template <class M> SC_FN bool scan_front(M& mem, int nIn, int capIn, ScanState& 
             if (fip + 128 < nI) mem.prefetch(fip + 128);
             nextEvt = ((fip >> 7) + 1) << 7;
         }
-        MARK_VISIT(fip, fop);
-        mem.tick(fip);                                             // (ring: top up every few iterations)
+        mem.tick(fip);
         mem.ensure(fip);                                           // [fip, fip + kMemAhead) is readable: token, short literals, offset
         const uint32_t v = mem.u32(fip);                           // token, then the 3 bytes that follow it
         const int mcode = (int)(v & 15u), lit4 = (int)((v >> 4) & 15u);
@@ -175,6 +176,7 @@ template <class M> SC_FN bool scan_front(M& mem, int nIn, int capIn, ScanState& 
         const bool exitC = (uint32_t)opn + (uint32_t)mlen >= (uint32_t)(capI - 64);   // lz4.c:2137/2142 -> safe_match_copy
         if (exitL || exitM || exitC) break;
         if (off16 > opn) { st.ip = ipn; st.nseq = nseq; return false; }       // lz4.c:2161
+        MARK_COMMIT(fip, opn);
         fip = ipn; fop = opn + mlen; nseq++;
     }
     st.ip = fip; st.op = fop; st.nseq = nseq;
@@ -186,12 +188,12 @@ template <class M> SC_FN bool scan_front(M& mem, int nIn, int capIn, ScanState& 
 template <class M> SC_FN int scan_tail(M& mem, int nIn, int capIn, const ScanState& st, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap)
 {
     int64_t nextPrefetch = st.nextPrefetch;
-    int64_t n = nIn, cap = capIn, ip = st.ip, op = st.op, ll = 0, ml = 0, add = 0;
+    int64_t n = nIn, cap = capIn, ip = st.ip, op = st.op, ll = 0, ml = 0, add = 0, tokPos = 0, mop = 0;
     uint32_t token = 0, offset = 0, nseq = st.nseq;
     bool fast = st.fast;
 
     for (;;) {
-        MARK_VISIT(ip, op);
+        tokPos = ip;                                                   /* this sequence's token; mop = where its match starts */
         if (ip + 128 >= nextPrefetch) {                               // keep the input one 128-byte line ahead in L1
             if (ip + 128 < n) mem.prefetch(ip + 128);
             nextPrefetch = ip + 256;
@@ -209,7 +211,7 @@ template <class M> SC_FN int scan_tail(M& mem, int nIn, int capIn, const ScanSta
             } else if (ip > n - 17) {
                 fast = false; goto safe_literals;
             }
-            ip += ll; op += ll;
+            ip += ll; op += ll; mop = op;
             mem.ensure(ip);
             offset = mem.u16(ip); ip += 2;
             if (ml == 15) {
@@ -219,16 +221,17 @@ template <class M> SC_FN int scan_tail(M& mem, int nIn, int capIn, const ScanSta
             ml += kMinMatch;
             if (op + ml >= cap - 64) { fast = false; goto safe_match; }
             if ((int64_t)offset > op) goto bad;                        // lz4.c:2161
+            MARK_COMMIT(tokPos, mop);
             op += ml; nseq++;
             continue;
         }
 
         /* safe loop, lz4.c:2215-2435 */
         if (ll != 15 && ip < n - 16 && op <= cap - 32) {               // two-stage shortcut :2230-2261
-            op += ll; ip += ll;
+            op += ll; ip += ll; mop = op;
             mem.ensure(ip);
             offset = mem.u16(ip); ip += 2;
-            if (ml != 15 && offset >= 8 && (int64_t)offset <= op) { op += ml + kMinMatch; nseq++; continue; }
+            if (ml != 15 && offset >= 8 && (int64_t)offset <= op) { MARK_COMMIT(tokPos, mop); op += ml + kMinMatch; nseq++; continue; }
             goto match_length;
         }
         if (ll == 15) {
@@ -238,11 +241,13 @@ template <class M> SC_FN int scan_tail(M& mem, int nIn, int capIn, const ScanSta
 safe_literals:
         if (op + ll > cap - kMfLimit || ip + ll > n - (2 + 1 + kLastLiterals)) {   // lz4.c:2279
             if (ip + ll != n || op + ll > cap) goto bad;               // lz4.c:2312
-            op += ll; nseq++;
+            op += ll;
+            MARK_COMMIT(tokPos, op);                                   /* last sequence: the end of its literals */
+            nseq++;
             *nSeqOut = nseq;
             return (int)op;                                            // lz4.c:2439
         }
-        ip += ll; op += ll;
+        ip += ll; op += ll; mop = op;
         mem.ensure(ip);
         offset = mem.u16(ip); ip += 2;
 match_length:
@@ -254,6 +259,7 @@ match_length:
 safe_match:
         if ((int64_t)offset > op) goto bad;                            // lz4.c:2356
         if (op + ml > cap - kLastLiterals) goto bad;                   // lz4.c:2421-2423
+        MARK_COMMIT(tokPos, mop);
         op += ml; nseq++;
     }
 bad:

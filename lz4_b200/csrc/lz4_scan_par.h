@@ -77,7 +77,6 @@ SC_FN void sp_walk(M& mem, int nI, int capI, int from, int segEnd,
             if (fip + 128 < nI) mem.prefetch(fip + 128);
             nextEvt = ((fip >> 7) + 1) << 7;
         }
-        if (WRITE) { const uint32_t nseq = seqBase + cnt; MARK_VISIT(fip, fop); }
         const uint32_t v = mem.u32(fip);
         const int mcode = (int)(v & 15u);
         int lit = (int)((v >> 4) & 15u), q = 1;
@@ -103,6 +102,7 @@ SC_FN void sp_walk(M& mem, int nI, int capI, int from, int segEnd,
         if (WRITE) {
             if (opn + (uint32_t)mlen >= (uint32_t)(capI - 64)) { kind = SP_END; break; }
             if (off16 > opn) { kind = SP_ERR; errIp = ipn; break; }
+            { const uint32_t nseq = seqBase + cnt; MARK_COMMIT(fip, opn); }
         }
         fip = ipn; fop = opn + (uint32_t)mlen; cnt++;
     }

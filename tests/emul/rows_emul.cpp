@@ -40,8 +40,7 @@ extern "C" int rows_emulate(const uint8_t* comp, int n, int cap, uint8_t* out, i
     std::vector<uint32_t> tab(kRowsMaxRuns, 0xDEADBEEFu);
 
     auto seq = [&](int k) {
-        const bool last = (k + 1 == nseq);
-        return rw_parse(in, marks[k], last ? 0u : marks[k + 1], k, last, total);
+        return rw_parse(in, marks[k], k, k + 1 == nseq);
     };
     // pass 1
     for (int tid = 0; tid < kThreads; tid++)

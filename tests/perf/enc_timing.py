@@ -34,6 +34,9 @@ def main():
     print("compress ms per launch %.3f, blocks %d, ratio %.4f" % (t0.elapsed_time(t1) / reps, n_blocks, n_blocks * bs / float(sizes.sum())))
     for n, v in zip(names, buf[:8]):
         print("%-28s %8.0f cycles/block  %5.1f%%" % (n, v / (reps * n_blocks), 100.0 * v / max(tot, 1)))
+    wins = max(buf[11], 1)
+    print("select: %.1f rounds per window, %.0f lane walks per window (1024 lanes), %d windows per block" % (
+        buf[8] / wins, buf[9] / wins, wins / ((reps + 1) * n_blocks)))
 
 
 if __name__ == "__main__":

@@ -47,10 +47,11 @@ def scan(tmp_path_factory):
 
 
 def true_marks(block):
-    """(token position | output position << 16) of every sequence of a VALID block, by a plain walk."""
+    """(token position | match start << 16) of every sequence of a VALID block (last sequence: the end of its
+    literals), by a plain walk."""
     b, n, p, o, out = bytes(block), len(block), 0, 0, []
     while True:
-        out.append((p & 0xFFFFFFFF) | ((o << 16) & 0xFFFFFFFF))
+        tokpos = p
         tok = b[p]
         p += 1
         ll = tok >> 4
@@ -63,6 +64,7 @@ def true_marks(block):
                     break
         p += ll
         o += ll
+        out.append((tokpos & 0xFFFFFFFF) | ((o << 16) & 0xFFFFFFFF))
         if p >= n:
             return out
         p += 2
