@@ -168,6 +168,16 @@ LZ4B200_API int LZ4B200_compress_blocks_parallel(const void* d_src, int64_t srcS
 LZ4B200_API int LZ4B200_pack_blocks(const void* d_slots, int64_t slotStride, const int32_t* d_sizes, int64_t nBlocks,
                                     void* d_packed, int64_t* d_outOff, int headerBytes, void* stream);
 
+/*
+ * The body of an LZ4 frame of independent blocks, assembled on the device (LZ4F_makeBlock, lz4frame.c:883-908):
+ * for every block [LE32 header][payload]; a block whose compressed size d_sizes[i] is 0 (it did not fit size - 1) or
+ * not smaller than its source is stored raw (payload = its source bytes from d_src + i*srcStride, bit 31 of the
+ * header set).  Block i has blockSize source bytes, the last one lastSize if lastSize > 0.  d_outOff[nBlocks] = body bytes.
+ */
+LZ4B200_API int LZ4B200_pack_frame_blocks(const void* d_slots, int64_t slotStride, const int32_t* d_sizes,
+                                          const void* d_src, int64_t srcStride, int32_t blockSize, int32_t lastSize,
+                                          int64_t nBlocks, void* d_body, int64_t* d_outOff, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * 3. Host-buffer batch calls (synchronous): the batch layer with the host<->device copies inside,
  *    pipelined over chunks.  h_* are host pointers (pinned memory gives full PCIe speed).

@@ -61,6 +61,7 @@ typedef struct {
     void* d_out[N_PIPE];  size_t out_cap[N_PIPE];
     void* d_meta[N_PIPE]; size_t meta_cap[N_PIPE];
     void* d_ws[N_PIPE];   size_t ws_cap[N_PIPE];
+    void* d_pack[N_PIPE]; size_t pack_cap[N_PIPE];   /* frame bodies assembled on the device */
     /* pinned host staging for the per-block tables, so that every copy of a chunk is truly
      * asynchronous (a pageable cudaMemcpyAsync blocks the host and serialises the pipeline) */
     void* h_meta[N_PIPE]; size_t hmeta_cap[N_PIPE];
@@ -200,6 +201,17 @@ int LZ4B200_pack_blocks(const void* d_slots, int64_t slotStride, const int32_t* 
     e = (cudaError_t)lz4k_launch_pack((const uint8_t*)d_slots, slotStride, d_sizes, nBlocks, (uint8_t*)d_packed,
                                       d_outOff, headerBytes, stream);
     return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "lz4k_launch_pack");
+}
+
+int LZ4B200_pack_frame_blocks(const void* d_slots, int64_t slotStride, const int32_t* d_sizes, const void* d_src, int64_t srcStride,
+                              int32_t blockSize, int32_t lastSize, int64_t nBlocks, void* d_body, int64_t* d_outOff, void* stream)
+{
+    cudaError_t e;
+    if (nBlocks < 0 || !d_outOff || blockSize <= 0 || lastSize < 0 || lastSize > blockSize) return LZ4B200_ERR_ARG;
+    if (nBlocks > 0 && (!d_slots || !d_sizes || !d_src || !d_body)) return LZ4B200_ERR_ARG;
+    e = (cudaError_t)lz4k_launch_pack_frame((const uint8_t*)d_slots, slotStride, d_sizes, (const uint8_t*)d_src, srcStride,
+                                            blockSize, lastSize, nBlocks, (uint8_t*)d_body, d_outOff, stream);
+    return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "lz4k_launch_pack_frame");
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -518,7 +530,7 @@ int64_t LZ4B200_compressFrame_host(const void* h_src, int64_t srcSize, void* h_d
 {
     const uint8_t* src = (const uint8_t*)h_src;
     uint8_t* dst = (uint8_t*)h_dst;
-    int64_t bs, nFull, lastSize, nBlocks, op = 0, first;
+    int64_t bs, nFull, lastSize, nBlocks, op = 0;
     int accel, bsid;
     if (srcSize < 0 || (!h_src && srcSize > 0) || !h_dst) return LZ4B200_ERR_ARG;
     if (blockSizeID == 0) blockSizeID = 4;
@@ -542,44 +554,66 @@ int64_t LZ4B200_compressFrame_host(const void* h_src, int64_t srcSize, void* h_d
     lastSize = srcSize - nFull * bs;
     nBlocks = nFull + (lastSize > 0);
     if (nBlocks > 0) {
-        /* blocks go through the batch layer in groups; each block is compressed with dstCapacity = size - 1,
-         * a result of 0 means "store raw" (LZ4F_makeBlock, lz4frame.c:883-908) */
+        /* Groups of ~256 MiB of source go through the device: H2D, one compress launch (dstCapacity = blockSize - 1; a
+         * result of 0 or >= the block's size means "store raw", LZ4F_makeBlock lz4frame.c:883-908), the frame body
+         * ([LE32 header][payload] per block) is assembled ON THE DEVICE, and one D2H per group lands it in h_dst.  Group
+         * g+1 is issued before group g is retired, so its copies and kernels overlap g's D2H. */
+        int64_t group = ((int64_t)256 << 20) / bs, nGroups, g;
         const int64_t slotStride = (bs + 15) & ~(int64_t)15;
-        int64_t group = ((int64_t)512 << 20) / bs;
-        uint8_t* slots;
-        int32_t* sizes;
+        int rc = LZ4B200_OK;
         if (group < 1) group = 1;
-        if (group > nBlocks) group = nBlocks;
-        slots = (uint8_t*)malloc((size_t)(group * slotStride));
-        sizes = (int32_t*)malloc((size_t)group * sizeof(int32_t));
-        if (!slots || !sizes) { free(slots); free(sizes); return LZ4B200_ERR_ARG; }
-        for (first = 0; first < nBlocks; first += group) {
-            const int64_t cnt = (nBlocks - first < group) ? nBlocks - first : group;
-            const int64_t fullInGroup = (first + cnt > nFull) ? nFull - first : cnt;   /* the ragged block, if any, is the last */
-            int64_t k;
-            int rc = LZ4B200_OK;
-            if (fullInGroup > 0)
-                rc = LZ4B200_compress_blocks_host(src + first * bs, bs, (int32_t)bs, bs, slots, slotStride, (int32_t)(bs - 1),
-                                                  accel, sizes, fullInGroup);
-            if (rc == LZ4B200_OK && fullInGroup < cnt)                    /* final short block: its own capacity */
-                rc = LZ4B200_compress_blocks_host(src + nFull * bs, lastSize, (int32_t)lastSize, lastSize,
-                                                  slots + fullInGroup * slotStride, slotStride, (int32_t)(lastSize - 1),
-                                                  accel, sizes + fullInGroup, 1);
-            if (rc != LZ4B200_OK) { free(slots); free(sizes); return rc; }
-            for (k = 0; k < cnt; k++) {
-                const int64_t blk = first + k;
-                const int64_t sz = (blk < nFull) ? bs : lastSize;
-                const int32_t c = sizes[k];
-                if (c <= 0 || c >= sz) {                                   /* lz4frame.c:896-899 */
-                    wr_le32(dst + op, (uint32_t)sz | 0x80000000u); op += 4;
-                    memcpy(dst + op, src + blk * bs, (size_t)sz); op += sz;
-                } else {
-                    wr_le32(dst + op, (uint32_t)c); op += 4;
-                    memcpy(dst + op, slots + k * slotStride, (size_t)c); op += c;
+        nGroups = (nBlocks + group - 1) / group;
+        pthread_mutex_lock(&g_lock);
+        if ((rc = ctx_init()) != LZ4B200_OK) { pthread_mutex_unlock(&g_lock); return rc; }
+        for (g = 0; g <= nGroups && rc == LZ4B200_OK; g++) {
+            if (g < nGroups) {                                         /* ---- issue group g ---- */
+                const int slot = (int)(g % N_PIPE);
+                const int64_t firstB = g * group;
+                const int64_t cnt = (nBlocks - firstB < group) ? nBlocks - firstB : group;
+                const int hasLast = (firstB + cnt == nBlocks) && lastSize > 0;
+                const int64_t inBytes = (cnt - 1) * bs + (hasLast ? lastSize : bs);
+                cudaStream_t st = g_ctx.stream[slot];
+                int64_t* d_off; int32_t* d_sz; int32_t* d_ssz;
+                if (cudaStreamSynchronize(st) != cudaSuccess) { rc = LZ4B200_ERR_CUDA; break; }
+                if ((rc = grow(&g_ctx.d_in[slot], &g_ctx.in_cap[slot], (size_t)inBytes + 16)) != LZ4B200_OK) break;
+                if ((rc = grow(&g_ctx.d_out[slot], &g_ctx.out_cap[slot], (size_t)(cnt * slotStride) + 16)) != LZ4B200_OK) break;
+                if ((rc = grow(&g_ctx.d_pack[slot], &g_ctx.pack_cap[slot], (size_t)(cnt * (bs + 4)) + 16)) != LZ4B200_OK) break;
+                if ((rc = grow(&g_ctx.d_meta[slot], &g_ctx.meta_cap[slot], (size_t)(cnt + 1) * 16 + 64)) != LZ4B200_OK) break;
+                if ((rc = grow_pinned(&g_ctx.h_meta[slot], &g_ctx.hmeta_cap[slot], (size_t)cnt * 4 + 64)) != LZ4B200_OK) break;
+                d_off = (int64_t*)g_ctx.d_meta[slot];
+                d_sz = (int32_t*)(d_off + cnt + 1);
+                d_ssz = d_sz + cnt;
+                if (cudaMemcpyAsync(g_ctx.d_in[slot], src + firstB * bs, (size_t)inBytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = LZ4B200_ERR_CUDA; break; }
+                if (hasLast) {                                           /* per-block sizes only for the group with the ragged block */
+                    int32_t* h_ssz = (int32_t*)((char*)g_ctx.h_meta[slot] + 64);
+                    int64_t k;
+                    for (k = 0; k < cnt; k++) h_ssz[k] = (int32_t)bs;
+                    h_ssz[cnt - 1] = (int32_t)lastSize;
+                    if (cudaMemcpyAsync(d_ssz, h_ssz, (size_t)cnt * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = LZ4B200_ERR_CUDA; break; }
                 }
+                rc = LZ4B200_compress_blocks(g_ctx.d_in[slot], bs, hasLast ? d_ssz : NULL, (int32_t)bs, g_ctx.d_out[slot], slotStride,
+                                             (int32_t)(bs - 1), accel, d_sz, cnt, st);
+                if (rc != LZ4B200_OK) break;
+                rc = LZ4B200_pack_frame_blocks(g_ctx.d_out[slot], slotStride, d_sz, g_ctx.d_in[slot], bs, (int32_t)bs,
+                                               hasLast ? (int32_t)lastSize : 0, cnt, g_ctx.d_pack[slot], d_off, st);
+                if (rc != LZ4B200_OK) break;
+                if (cudaMemcpyAsync(g_ctx.h_meta[slot], d_off + cnt, sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = LZ4B200_ERR_CUDA; break; }
+            }
+            if (g > 0) {                                               /* ---- retire group g-1: its size is known once its stream is idle ---- */
+                const int slot = (int)((g - 1) % N_PIPE);
+                cudaStream_t st = g_ctx.stream[slot];
+                int64_t total;
+                if (cudaStreamSynchronize(st) != cudaSuccess) { rc = LZ4B200_ERR_CUDA; break; }
+                total = *(const int64_t*)g_ctx.h_meta[slot];
+                if (op + total + 4 > dstCapacity) { rc = LZ4B200_ERR_DSTSIZE; break; }
+                if (cudaMemcpyAsync(dst + op, g_ctx.d_pack[slot], (size_t)total, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = LZ4B200_ERR_CUDA; break; }
+                op += total;
             }
         }
-        free(slots); free(sizes);
+        {   int i; for (i = 0; i < N_PIPE; i++) if (cudaStreamSynchronize(g_ctx.stream[i]) != cudaSuccess && rc == LZ4B200_OK) rc = LZ4B200_ERR_CUDA; }
+        pthread_mutex_unlock(&g_lock);
+        if (rc == LZ4B200_ERR_CUDA) cuda_fail(cudaGetLastError(), "LZ4B200_compressFrame_host");
+        if (rc != LZ4B200_OK) return rc;
     }
     wr_le32(dst + op, 0); op += 4;                                        /* EndMark, lz4frame.c:1222 */
     return op;

@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
     const int r = scan_block(mem, n, cap, &ns, marks, w.markStride);
     a.outSize[b] = r;
     w.nSeq[b] = ns;
+#ifdef LZ4K_PF_LOAD
+    if ((mem.sink ^ mem.pend) == 0x9E3779B9u && ns == 0x7FFFFFFFu) w.nSeq[b] = 0;       /* keeps the experiment's loads alive */
+#endif
     if (r > 0 && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
 }
 
@@ -173,8 +176,12 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
  * Lists go to the scratch part of the workspace (2 x markStride words per block), the per-block records to shared memory. */
 constexpr int kSplitThreads = 128;
 constexpr int kSplitBlocksPerCta = kSplitThreads / kSsLanes;
+constexpr int64_t kSplitMaxBlocks = 8192;         /* largest batch the split scan is the default for */
 
-__global__ void __launch_bounds__(kSplitThreads, 10) lz4_scan_split_kernel(lz4k_decode_args a)
+#ifndef LZ4K_SS_MINB
+#define LZ4K_SS_MINB 10
+#endif
+__global__ void __launch_bounds__(kSplitThreads, LZ4K_SS_MINB) lz4_scan_split_kernel(lz4k_decode_args a)
 {
     __shared__ SsBlock sh[kSplitBlocksPerCta];
     const int lane = threadIdx.x % kSsLanes, slot = threadIdx.x / kSsLanes;
@@ -955,9 +962,24 @@ __global__ void __launch_bounds__(32) lz4_encode_kernel(lz4k_encode_args a)
 
 /* =============================================================================================
  * pack: exclusive scan of sizes (+ optional 4-byte headers) and gather into a contiguous stream
+ * With a FrameRule the blocks become the body of an LZ4 frame (LZ4F_makeBlock, lz4frame.c:883-908): a block whose
+ * compression did not gain (size 0 = did not fit size-1, or >= its source size) is stored raw -- payload = the
+ * source bytes, bit 31 of the LE32 block header set.
  * ============================================================================================= */
+struct FrameRule { const uint8_t* raw; int64_t rawStride; int32_t blockSize, lastSize; };     /* raw == nullptr: plain pack */
+
+__device__ __forceinline__ int pack_payload(const FrameRule& fr, const int32_t* sizes, int64_t b, int64_t n, bool& isRaw)
+{
+    const int c = sizes[b];
+    isRaw = false;
+    if (!fr.raw) return c > 0 ? c : 0;
+    const int sz = (b == n - 1 && fr.lastSize > 0) ? fr.lastSize : fr.blockSize;
+    isRaw = (c <= 0 || c >= sz);                                /* lz4frame.c:896-899 */
+    return isRaw ? sz : c;
+}
+
 __global__ void __launch_bounds__(1024) lz4_pack_scan_kernel(const int32_t* __restrict__ sizes, int64_t n,
-                                                             int64_t* __restrict__ outOff, int headerBytes)
+                                                             int64_t* __restrict__ outOff, int headerBytes, FrameRule fr)
 {
     __shared__ int64_t warpSums[32];
     __shared__ int64_t carry;
@@ -967,7 +989,7 @@ __global__ void __launch_bounds__(1024) lz4_pack_scan_kernel(const int32_t* __re
     for (int64_t base = 0; base < n; base += 1024) {
         int64_t i = base + threadIdx.x;
         int64_t v = 0;
-        if (i < n) { int s = sizes[i]; v = (s > 0 ? s : 0) + headerBytes; }
+        if (i < n) { bool isRaw; v = pack_payload(fr, sizes, i, n, isRaw) + headerBytes; }
         int64_t x = v;
         for (int d = 1; d < 32; d <<= 1) { int64_t y = __shfl_up_sync(kFull, x, d); if (lane >= d) x += y; }
         if (lane == 31) warpSums[wid] = x;
@@ -990,13 +1012,15 @@ __global__ void __launch_bounds__(1024) lz4_pack_scan_kernel(const int32_t* __re
 __global__ void __launch_bounds__(256) lz4_pack_gather_kernel(const uint8_t* __restrict__ slots, int64_t slotStride,
                                                               const int32_t* __restrict__ sizes, int64_t n,
                                                               uint8_t* __restrict__ packed, const int64_t* __restrict__ outOff,
-                                                              int headerBytes)
+                                                              int headerBytes, FrameRule fr)
 {
     for (int64_t b = blockIdx.x; b < n; b += gridDim.x) {
-        const int s = sizes[b] > 0 ? sizes[b] : 0;
-        const uint8_t* from = slots + b * slotStride;
+        bool isRaw;
+        const int s = pack_payload(fr, sizes, b, n, isRaw);
+        const uint8_t* from = isRaw ? fr.raw + b * fr.rawStride : slots + b * slotStride;
         uint8_t* to = packed + outOff[b];
-        if (headerBytes == 4 && threadIdx.x < 4) to[threadIdx.x] = (uint8_t)((uint32_t)s >> (8 * threadIdx.x));   // lz4frame.c:896-907 LE32
+        const uint32_t hw = (uint32_t)s | (isRaw ? 0x80000000u : 0u);
+        if (headerBytes == 4 && threadIdx.x < 4) to[threadIdx.x] = (uint8_t)(hw >> (8 * threadIdx.x));   // lz4frame.c:896-907 LE32
         to += headerBytes;
         /* destination-aligned 16-byte stores, source read through aligned words */
         const uintptr_t ta = reinterpret_cast<uintptr_t>(to);
@@ -1084,8 +1108,12 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         /* measured (profiles/): the lanes of the parallel scan re-walk their segments several times, ~10x the instructions of the
          * one-thread scan, so it only pays for blocks far beyond 64 KB (lz4frame's 4 MB blocks: 150 000 dependent steps for one thread) */
         const bool par = scanImpl >= 0 ? scanImpl == 1 : (a->dstCapArr == nullptr && a->dstCap > 65536);
-        /* blocks of 16..64 KB: kSsLanes merging lanes per block; smaller blocks have too few sequences to split */
-        const bool split = scanImpl >= 0 ? scanImpl == 2 : (a->dstCapArr == nullptr && a->dstCap >= 16384 && a->dstCap <= 65536);
+        /* blocks of 16..64 KB: kSsLanes merging lanes per block (smaller blocks have too few sequences to split).  Measured
+         * (profiles/README.md): faster than one thread per block while the batch leaves SMs idle (1.31 against 1.85 ms for
+         * 8192 blocks), slower once the one-thread scan fills them (7.4 against 2.7 ms for 65536 blocks: four times the
+         * threads, each with its own cache lines in flight, overflow L1) */
+        const bool split = scanImpl >= 0 ? scanImpl == 2
+                                         : (a->dstCapArr == nullptr && a->dstCap >= 16384 && a->dstCap <= 65536 && a->nBlocks <= kSplitMaxBlocks);
         if (split && !par) {
             const int64_t grid = (a->nBlocks + kSplitBlocksPerCta - 1) / kSplitBlocksPerCta;
             lz4_scan_split_kernel<<<(unsigned)grid, kSplitThreads, 0, s>>>(*a);
@@ -1151,11 +1179,28 @@ int lz4k_launch_pack(const uint8_t* slots, int64_t slotStride, const int32_t* si
                      uint8_t* packed, int64_t* outOff, int headerBytes, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
-    lz4_pack_scan_kernel<<<1, 1024, 0, s>>>(sizes, nBlocks, outOff, headerBytes);
+    FrameRule fr; fr.raw = nullptr; fr.rawStride = 0; fr.blockSize = 0; fr.lastSize = 0;
+    lz4_pack_scan_kernel<<<1, 1024, 0, s>>>(sizes, nBlocks, outOff, headerBytes, fr);
     g_launches++;
     if (nBlocks > 0) {
         int64_t grid = nBlocks < 148 * 16 ? nBlocks : 148 * 16;
-        lz4_pack_gather_kernel<<<(unsigned)grid, 256, 0, s>>>(slots, slotStride, sizes, nBlocks, packed, outOff, headerBytes);
+        lz4_pack_gather_kernel<<<(unsigned)grid, 256, 0, s>>>(slots, slotStride, sizes, nBlocks, packed, outOff, headerBytes, fr);
+        g_launches++;
+    }
+    return (int)cudaGetLastError();
+}
+
+/* frame body: [LE32 header][payload] per block, stored-raw rule applied on the device (src = the blocks' source bytes) */
+int lz4k_launch_pack_frame(const uint8_t* slots, int64_t slotStride, const int32_t* sizes, const uint8_t* src, int64_t srcStride,
+                           int32_t blockSize, int32_t lastSize, int64_t nBlocks, uint8_t* packed, int64_t* outOff, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    FrameRule fr; fr.raw = src; fr.rawStride = srcStride; fr.blockSize = blockSize; fr.lastSize = lastSize;
+    lz4_pack_scan_kernel<<<1, 1024, 0, s>>>(sizes, nBlocks, outOff, 4, fr);
+    g_launches++;
+    if (nBlocks > 0) {
+        int64_t grid = nBlocks < 148 * 16 ? nBlocks : 148 * 16;
+        lz4_pack_gather_kernel<<<(unsigned)grid, 256, 0, s>>>(slots, slotStride, sizes, nBlocks, packed, outOff, 4, fr);
         g_launches++;
     }
     return (int)cudaGetLastError();

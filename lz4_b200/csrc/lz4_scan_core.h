@@ -50,7 +50,14 @@ constexpr int kMfLimit = 12;
  * read; they are no-ops for both kinds (they served a per-thread shared-memory ring fed by cp.async, measured in round 2
  * and dropped: 2.8 - 6.8 ms against 2.6 ms for the plain loads, profiles/README.md).
  * ------------------------------------------------------------------------------------------- */
-constexpr int kMemAhead = 32;              /* bytes that ensure(i) makes readable: [i, i + kMemAhead) */
+constexpr int kMemAhead = 32;
+/* L1 prefetch of the walk: one hint per 2^LZ4K_PF_STEP_LOG input bytes, LZ4K_PF_DIST bytes ahead */
+#ifndef LZ4K_PF_STEP_LOG
+#define LZ4K_PF_STEP_LOG 7
+#endif
+#ifndef LZ4K_PF_DIST
+#define LZ4K_PF_DIST 128
+#endif              /* bytes that ensure(i) makes readable: [i, i + kMemAhead) */
 
 template <bool G> SC_FN uint32_t ldb(const uint8_t* p) { return G ? (uint32_t)SC_LDG(p) : (uint32_t)*p; }
 template <bool G> SC_FN uint32_t ldw(const uint32_t* p) { return G ? SC_LDG(p) : *p; }
@@ -75,7 +82,16 @@ template <bool G> struct MemPtr {
     SC_MFN uint32_t u32(int64_t i) const { return ld32u<G>(p + i); }
     SC_MFN void ensure(int64_t) const { }
     SC_MFN void tick(int64_t) const { }
+#if defined(LZ4K_PF_LOAD) && defined(__CUDACC__)
+    /* experiment: the hint is a real load whose value is folded into `sink` one hint later */
+    mutable uint32_t pend = 0, sink = 0;
+    SC_MFN void prefetch(int64_t i) const
+    {
+        if (G) { sink ^= pend; pend = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p + i) & ~uintptr_t(3))); }
+    }
+#else
     SC_MFN void prefetch(int64_t i) const { if (G) SC_PREFETCH_L1(p + i); }
+#endif
     static constexpr bool kPrefetch = G;
 };
 
@@ -139,9 +155,9 @@ template <class M> SC_FN bool scan_front(M& mem, int nIn, int capIn, ScanState& 
      * (literal runs < 525 bytes, matches < 529); longer ones go round the reference's loops, which are skipped
      * (condition false for every lane) otherwise.  The exits are collected and taken once, in the reference's order. */
     while (fip <= nI - 26) {
-        if (M::kPrefetch && fip >= nextEvt) {                      // L1 prefetch, once per 128 input bytes
-            if (fip + 128 < nI) mem.prefetch(fip + 128);
-            nextEvt = ((fip >> 7) + 1) << 7;
+        if (M::kPrefetch && fip >= nextEvt) {                      // L1 prefetch hint
+            if (fip + LZ4K_PF_DIST < nI) mem.prefetch(fip + LZ4K_PF_DIST);
+            nextEvt = ((fip >> LZ4K_PF_STEP_LOG) + 1) << LZ4K_PF_STEP_LOG;
         }
         mem.tick(fip);
         mem.ensure(fip);                                           // [fip, fip + kMemAhead) is readable: token, short literals, offset

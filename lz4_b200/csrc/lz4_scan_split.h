@@ -132,7 +132,12 @@ SC_FN void ss_p1(int lane, SsBlock& S, M& mem, int nI, uint32_t* A, uint32_t* B,
     int fip = ss_seg_start(lane, nI);
     uint32_t fop = 0;
     me.cnt = 0; me.state = SS_RUN; me.inChain = 0; me.target = -1;
+    int nextEvt = 0;
     while (fip < segEnd) {
+        if (M::kPrefetch && fip >= nextEvt) {
+            if (fip + LZ4K_PF_DIST < nI) mem.prefetch(fip + LZ4K_PF_DIST);
+            nextEvt = ((fip >> LZ4K_PF_STEP_LOG) + 1) << LZ4K_PF_STEP_LOG;
+        }
         int ipn, lit, mlen; uint32_t off16;
         if (!ss_step(mem, nI, fip, ipn, lit, mlen, off16)) { me.state = SS_STOP; break; }
         if (!ss_push(me, A, B, R, fip, off16, fop + (uint32_t)lit)) break;
