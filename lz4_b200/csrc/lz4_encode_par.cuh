@@ -11,11 +11,13 @@
  * LZ4B200_compress_blocks.
  *
  * A block of n <= 65 536 bytes is staged in shared memory by one TMA bulk load, then processed in WINDOWS
- * of 16 384 positions; thread t of 1024 owns the 16 consecutive positions 16t .. 16t+15 of the window:
+ * of 8192 positions; thread t of 512 owns the 16 consecutive positions 16t .. 16t+15 of the window (two CTAs share an
+ * SM: 102 KB of shared memory each -- the block, two 16-bit tables of 8192 entries, the window's output assembled in
+ * the bytes of the second table -- so that one CTA's barrier waits are the other's issue slots):
  *
  *   find    every position hashes its 4 bytes (Fibonacci hash, 13 bits: lz4.c:779).  T[h] holds the LATEST
  *           position of an EARLIER window with that hash, T2[h] the EARLIEST position of THIS window
- *           (atomicMax on a window-tagged complement): both are scheduling-independent.  A position's
+ *           (atomicMax on the complement of its index): both are scheduling-independent.  A position's
  *           candidate is, in this order: p-d if the 5 bytes at p repeat at distance d <= 4 (RLE-like data,
  *           where one table slot per hash cannot serve every position), T2's position if it lies before p
  *           and its 4 bytes match, T's.  One bit per position says "has a candidate".
@@ -36,29 +38,49 @@
  */
 #pragma once
 
-constexpr int kEpThreads = 1024;
+constexpr int kEpThreads = 512;                      /* two CTAs per SM: one CTA's barrier waits are the other's issue slots */
+constexpr int kEpWarps = kEpThreads / 32;
 constexpr int kEpPer = 16;                           /* positions per thread and window */
-constexpr int kEpWin = kEpThreads * kEpPer;          /* 16 384 positions per window */
+constexpr int kEpWin = kEpThreads * kEpPer;          /* 8192 positions per window */
 constexpr int kEpHashLog = 13;
 constexpr int kEpMaxSel = kEpPer / 4;                /* matches are >= 4 long: at most 4 selections per lane */
 constexpr int kEpSolo = 32;                          /* bytes a lane compares alone (> kEpPer: a longer match ends the lane's walk) */
 constexpr int kEpInlineLits = 32;                    /* literal runs up to this length are copied by the emitting thread */
-constexpr int kEpMaxLitJobs = 512;                   /* (at most 16384/33 longer literal runs end in a window) */
-constexpr int kEpStage = 32768;                      /* a window's output is assembled here when it fits */
+constexpr int kEpMaxLitJobs = 256;                   /* (at most 8192/33 longer literal runs end in a window) */
+constexpr int kEpStage = 2 << kEpHashLog;            /* a window's output is assembled here (the bytes of T2) when it fits */
 
 struct EncParSmem {
     alignas(16) uint8_t pad[16];                     /* the 4 bytes "before" position 0 are read (never used) */
     alignas(16) uint8_t src[65536 + 64];             /* staged block (keeps the source's 16-byte phase) */
-    uint32_t T[1 << kEpHashLog];                     /* latest position + 1 of an earlier window, per hash */
-    uint32_t T2[1 << kEpHashLog];                    /* (window + 1) << 16 | (0xFFFF - index in window): earliest of this window */
+    alignas(16) uint16_t T[1 << kEpHashLog];         /* latest position + 1 of an earlier window, per hash (0: none) */
+    union {                                          /* find + select use T2; emit assembles the window's output in the same bytes and clears them */
+        alignas(16) uint16_t T2[1 << kEpHashLog];    /* 0xFFFF - index in window of the EARLIEST position of this window, per hash (0: none) */
+        alignas(16) uint8_t stage[kEpStage];
+    };
     uint32_t litJob[kEpMaxLitJobs][3];               /* {source position, output offset, length} */
-    alignas(16) uint8_t stage[kEpStage];
-    int warpLast[32];                                /* chain scan: end of the last match selected in each warp, or -1 */
-    uint32_t warpSum[32];
+    int warpLast[kEpWarps];                          /* chain scan: end of the last match selected in each warp, or -1 */
+    uint32_t warpSum[kEpWarps];
     uint32_t nLitJobs, E, O, fail;
     alignas(8) uint64_t mbar;
 };
-static_assert(sizeof(EncParSmem) <= 232448, "EncParSmem exceeds the shared memory a CTA can opt in to");
+static_assert(sizeof(EncParSmem) <= (232448 - 2048) / 2, "two CTAs of the parallel compressor must fit one SM");
+
+/* atomicMax on a 16-bit shared-memory cell (CAS on the 32-bit word that holds it); the final value is the maximum of all
+ * values offered, whatever the order: scheduling-independent */
+__device__ __forceinline__ void ep_atomic_max_u16(uint16_t* cell, uint32_t v)
+{
+    const uintptr_t u = reinterpret_cast<uintptr_t>(cell);
+    uint32_t* w = reinterpret_cast<uint32_t*>(u & ~uintptr_t(3));
+    const uint32_t sh = (uint32_t)(u & 2u) * 8u;
+    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(w);
+    for (;;) {
+        if (((cur >> sh) & 0xFFFFu) >= v) return;
+        const uint32_t nw = (cur & ~(0xFFFFu << sh)) | (v << sh);
+        const uint32_t old = atomicCAS(w, cur, nw);
+        if (old == cur) return;
+        cur = old;
+    }
+}
 
 __device__ __forceinline__ uint32_t ep_ld32(const uint8_t* base, uint32_t i)      /* unaligned 4 bytes at base + i (base 4-aligned) */
 {
@@ -95,8 +117,8 @@ __device__ __forceinline__ uint32_t ep_table_candidate(const EncParSmem& S, cons
 {
     const uint32_t h = ep_hash(v);
     const uint32_t e = S.T2[h];
-    const int q = c0 + (0xFFFF - (int)(e & 0xFFFFu));                              /* earliest position of this window with this hash */
-    if (q < p && ep_ld32(src, (uint32_t)(head + q)) == v) return (uint32_t)q;
+    const int q = c0 + (0xFFFF - (int)e);                                          /* earliest position of this window with this hash */
+    if (e && q < p && ep_ld32(src, (uint32_t)(head + q)) == v) return (uint32_t)q;
     const uint32_t o = S.T[h];
     if (o && ep_ld32(src, (uint32_t)head + o - 1u) == v) return o - 1u;
     return 0xFFFFFFFFu;
@@ -129,7 +151,7 @@ __device__ __forceinline__ int ep_extend(const uint8_t* src, int head, int p, ui
     return L > limit ? limit : L;
 }
 
-__global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_encode_args a)
+__global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_encode_args a)
 {
     extern __shared__ __align__(16) uint8_t smemRaw[];
     EncParSmem& S = *reinterpret_cast<EncParSmem*>(smemRaw);
@@ -159,7 +181,10 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
             for (uint32_t o = 0; o < loadBytes; o += 16384u) tma_load_1d(S.src + o, gsrc - head + o, min(16384u, loadBytes - o), &S.mbar);
             S.E = 0; S.O = 0; S.fail = 0; S.nLitJobs = 0;
         }
-        for (int k = tid; k < (1 << kEpHashLog); k += kEpThreads) { S.T[k] = 0; S.T2[k] = 0; }
+        for (int k = tid; k < (1 << kEpHashLog) / 8; k += kEpThreads) {
+            reinterpret_cast<uint4*>(S.T)[k] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4*>(S.T2)[k] = make_uint4(0, 0, 0, 0);
+        }
         __syncthreads();
         mbar_wait(&S.mbar, parity);
         parity ^= 1;
@@ -177,7 +202,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
             #pragma unroll
             for (int i = 0; i < kEpPer; i++)
                 if (i < cnt && (step == 1 || (p0 + i) % step == 0))
-                    atomicMax(&S.T2[ep_hash(by.val(i))], ((uint32_t)(w + 1) << 16) | (uint32_t)(0xFFFF - (i0 + i)));
+                    ep_atomic_max_u16(&S.T2[ep_hash(by.val(i))], (uint32_t)(0xFFFF - (i0 + i)));
             __syncthreads();
             PHASE_MARK(0);                                     // find 1
             /* ---------------- find 2: which positions have a candidate ---------------- */
@@ -300,7 +325,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
             if (nSel) sLit[0] = eCur;                                     /* the first one's literals start at the true entry */
             if (tid == kEpThreads - 1) {                                 /* the chain's position after this window */
                 int last = nSel ? exitE : -1;
-                for (int q = 31; q >= 0 && last < 0; q--) last = S.warpLast[q];
+                for (int q = kEpWarps - 1; q >= 0 && last < 0; q--) last = S.warpLast[q];
                 S.E = (uint32_t)(last < 0 ? Ein : last);
             }
             PHASE_MARK(4);                                     // select
@@ -325,9 +350,11 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 __syncthreads();
                 const uint32_t O0 = S.O;
                 uint32_t base = O0, winTotal = 0;
-                for (int q = 0; q < 32; q++) { const uint32_t x = S.warpSum[q]; winTotal += x; if (q < warp) base += x; }
-                const bool staged = winTotal <= (uint32_t)kEpStage;
-                uint8_t* const obase = staged ? S.stage - O0 : dst;             /* output offset o lives at obase + o */
+                for (int q = 0; q < kEpWarps; q++) { const uint32_t x = S.warpSum[q]; winTotal += x; if (q < warp) base += x; }
+                /* (a window's output can exceed its 8192 positions: its first sequence carries the literals of earlier windows) */
+                const bool staged = winTotal + 16u <= (uint32_t)kEpStage;
+                const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst + O0) & 15u);   /* stage keeps the 16-byte phase of the destination */
+                uint8_t* const obase = staged ? S.stage + mis - O0 : dst;       /* output offset o lives at obase + o */
                 int64_t o = (int64_t)base + incl - size;
                 if (size && o + size > cap) S.fail = 1;
                 else {
@@ -356,7 +383,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 __syncthreads();
                 if (tid == 0) S.O = O0 + winTotal;
                 const uint32_t nLit = S.nLitJobs;
-                for (uint32_t j = warp; j < nLit; j += 32) {
+                for (uint32_t j = warp; j < nLit; j += kEpWarps) {
                     const uint32_t from = S.litJob[j][0], to = S.litJob[j][1], cntL = S.litJob[j][2];
                     for (uint32_t i = lane; i < cntL; i += 32) obase[to + i] = src[head + from + i];
                 }
@@ -364,10 +391,27 @@ __global__ void __launch_bounds__(kEpThreads, 1) lz4_encode_par_kernel(lz4k_enco
                 #pragma unroll
                 for (int i = 0; i < kEpPer; i++)
                     if (i < cnt && (step == 1 || (p0 + i) % step == 0))
-                        atomicMax(&S.T[ep_hash(by.val(i))], (uint32_t)(p0 + i) + 1u);
+                        ep_atomic_max_u16(&S.T[ep_hash(by.val(i))], (uint32_t)(p0 + i) + 1u);
                 __syncthreads();
-                if (staged && !S.fail)                                           /* coalesced: consecutive threads, consecutive bytes */
-                    for (uint32_t i = tid; i < winTotal; i += kEpThreads) dst[O0 + i] = S.stage[i];
+                /* write the window out in aligned 16-byte pieces and hand the bytes back to T2, cleared */
+                {
+                    const bool put = staged && !S.fail;
+                    uint8_t* const gbase = dst + O0 - mis;                        /* 16-byte aligned; stage byte i belongs at gbase + i */
+                    for (uint32_t c = tid; c < (uint32_t)kEpStage / 16u; c += kEpThreads) {
+                        const uint4 v = reinterpret_cast<const uint4*>(S.stage)[c];
+                        reinterpret_cast<uint4*>(S.stage)[c] = make_uint4(0, 0, 0, 0);
+                        const uint32_t lo = c * 16u;
+                        if (put && lo + 16u > mis && lo < mis + winTotal) {
+                            if (lo >= mis && lo + 16u <= mis + winTotal) *reinterpret_cast<uint4*>(gbase + lo) = v;
+                            else {
+                                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                                #pragma unroll
+                                for (uint32_t i = 0; i < 16u; i++)
+                                    if (lo + i >= mis && lo + i < mis + winTotal) gbase[lo + i] = (uint8_t)(wv[i >> 2] >> ((i & 3u) * 8u));
+                            }
+                        }
+                    }
+                }
                 if (tid == 0) S.nLitJobs = 0;
                 __syncthreads();
                 PHASE_MARK(5);                                 // emit + insert

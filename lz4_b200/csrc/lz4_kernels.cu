@@ -150,9 +150,16 @@ __device__ __forceinline__ bool rows_eligible(int n, int cap, uint32_t nseq, uin
 }
 
 /* ---- scan, one THREAD per block: reads through the read-only data cache with L1 prefetch hints ---- */
+#ifndef LZ4K_SCAN_LANE_STRIDE
+#define LZ4K_SCAN_LANE_STRIDE 1
+#endif
 __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
 {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#if LZ4K_SCAN_LANE_STRIDE > 1
+    if (b % LZ4K_SCAN_LANE_STRIDE) return;               /* experiment: fewer blocks per warp = fewer distinct paths per step */
+    b /= LZ4K_SCAN_LANE_STRIDE;
+#endif
     if (b >= a.nBlocks) return;
     const WsView w = ws_view(a);
     const uint8_t* src = a.src + a.srcOff[b];
@@ -1123,7 +1130,7 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
             lz4_scan_par_kernel<<<(unsigned)grid, kScanLanes, sizeof(ScanParSmem), s>>>(*a);
         } else {
             const int threads = 128;
-            const int64_t grid = (a->nBlocks + threads - 1) / threads;
+            const int64_t grid = (a->nBlocks * LZ4K_SCAN_LANE_STRIDE + threads - 1) / threads;
             lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
         }
         g_launches++;
@@ -1169,7 +1176,7 @@ int lz4k_launch_encode_par(const lz4k_encode_args* a, void* stream)
         if (e != cudaSuccess) return (int)e;
         sms = v;
     }
-    const int64_t grid = a->nBlocks < sms ? a->nBlocks : sms;        // persistent: one CTA per SM, blocks c, c + grid, ...
+    const int64_t grid = a->nBlocks < 2 * sms ? a->nBlocks : 2 * sms;        // persistent: two CTAs per SM, blocks c, c + grid, ...
     lz4_encode_par_kernel<<<(unsigned)grid, kEpThreads, sizeof(EncParSmem), s>>>(*a);
     g_launches++;
     return (int)cudaGetLastError();

@@ -36,6 +36,15 @@ static inline uint32_t sc_funnel_r_host(uint32_t lo, uint32_t hi, uint32_t s)
 #define SC_PREFETCH_L1(p) ((void)(p))
 #endif
 
+/* stores of marks / scratch lists and reads of scratch lists: experiment LZ4K_ST_CG keeps them out of L1 (cache-global) */
+#if defined(__CUDACC__) && defined(LZ4K_ST_CG)
+#define SC_ST(p, v) __stcg((p), (v))
+#define SC_LD_SCRATCH(p) __ldcg(p)
+#else
+#define SC_ST(p, v) (*(p) = (v))
+#define SC_LD_SCRATCH(p) (*(p))
+#endif
+
 #ifndef LZ4_SCAN_CORE_CONSTANTS
 constexpr int kMinMatch = 4;
 constexpr int kLastLiterals = 5;
@@ -126,7 +135,7 @@ constexpr int kMaxSeqFast = 8192;              // most sequences a block of the 
 /* `markCap` = number of mark slots the caller reserved for this block (<= kMaxSeqFast); a block that can be
  * expanded from shared memory has at most capacity/4 + 1 sequences (every sequence but the last makes >= 4 bytes) */
 #define MARK_COMMIT(tokpos, matchpos)                                                           \
-    do { if (marks && nseq < markCap) marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(matchpos) << 16); } while (0)
+    do { if (marks && nseq < markCap) SC_ST(&marks[nseq], (uint32_t)(tokpos) | ((uint32_t)(matchpos) << 16)); } while (0)
 
 /* where the walk of one block stands between its two loops */
 struct ScanState {
