@@ -12,15 +12,15 @@
  *
  * A block of n <= 65 536 bytes is staged in shared memory by one TMA bulk load, then processed in WINDOWS
  * of 8192 positions; thread t of 512 owns the 16 consecutive positions 16t .. 16t+15 of the window (two CTAs share an
- * SM: 102 KB of shared memory each -- the block, two 16-bit tables of 8192 entries, the window's output assembled in
- * the bytes of the second table -- so that one CTA's barrier waits are the other's issue slots):
+ * SM: 110 KB of shared memory each -- the block, one 8192-word table, the window's output -- so that one CTA's
+ * barrier waits are the other's issue slots):
  *
- *   find    every position hashes its 4 bytes (Fibonacci hash, 13 bits: lz4.c:779).  T[h] holds the LATEST
- *           position of an EARLIER window with that hash, T2[h] the EARLIEST position of THIS window
- *           (atomicMax on the complement of its index): both are scheduling-independent.  A position's
+ *   find    every position hashes its 4 bytes (Fibonacci hash, 13 bits: lz4.c:779).  The table word of a hash holds
+ *           the LATEST position of an EARLIER window (low half) and the EARLIEST position of THIS window (high half,
+ *           atomicMax on the complement of its index): both are scheduling-independent.  A position's
  *           candidate is, in this order: p-d if the 5 bytes at p repeat at distance d <= 4 (RLE-like data,
- *           where one table slot per hash cannot serve every position), T2's position if it lies before p
- *           and its 4 bytes match, T's.  One bit per position says "has a candidate".
+ *           where one table slot per hash cannot serve every position), this window's earliest position if it lies
+ *           before p and its 4 bytes match, the earlier windows' latest.  One bit per position says "has a candidate".
  *   select  the reference's greedy rule -- the first position at or after the end of the previous match that
  *           has a candidate is taken, with its longest match (lz4.c:1014-1100, 1182) -- evaluated by all lanes at
  *           once: every lane walks its 16 positions as if the chain entered at its first position, a CTA-wide
@@ -30,7 +30,7 @@
  *   emit    backward extension (lz4.c:1107-1109), sizes, CTA-wide exclusive sum; a window's output is assembled in
  *           shared memory and written out as consecutive bytes (scattered byte stores to HBM cost a transaction
  *           each); literal runs above 32 bytes are copied by a whole warp.
- *   insert  the window's positions enter T (atomicMax).
+ *   insert  the window's positions enter the low halves (atomicMax, after the high halves are cleared).
  *
  * The end-of-block rules of the format are the reference's: no match starts after n-12, the last 5 bytes
  * are literals (lz4.c:963-964, 1233); output that does not fit dstCapacity makes the call return 0.
@@ -47,16 +47,17 @@ constexpr int kEpMaxSel = kEpPer / 4;                /* matches are >= 4 long: a
 constexpr int kEpSolo = 32;                          /* bytes a lane compares alone (> kEpPer: a longer match ends the lane's walk) */
 constexpr int kEpInlineLits = 32;                    /* literal runs up to this length are copied by the emitting thread */
 constexpr int kEpMaxLitJobs = 256;                   /* (at most 8192/33 longer literal runs end in a window) */
-constexpr int kEpStage = 2 << kEpHashLog;            /* a window's output is assembled here (the bytes of T2) when it fits */
+constexpr int kEpStage = kEpWin + 512;               /* a window's output is assembled here when it fits (it does unless literals of earlier windows come with it) */
 
 struct EncParSmem {
     alignas(16) uint8_t pad[16];                     /* the 4 bytes "before" position 0 are read (never used) */
     alignas(16) uint8_t src[65536 + 64];             /* staged block (keeps the source's 16-byte phase) */
-    alignas(16) uint16_t T[1 << kEpHashLog];         /* latest position + 1 of an earlier window, per hash (0: none) */
-    union {                                          /* find + select use T2; emit assembles the window's output in the same bytes and clears them */
-        alignas(16) uint16_t T2[1 << kEpHashLog];    /* 0xFFFF - index in window of the EARLIEST position of this window, per hash (0: none) */
-        alignas(16) uint8_t stage[kEpStage];
-    };
+    /* per hash, one word: low half = latest position + 1 of an EARLIER window (0: none); high half = 0xFFFF - index in
+     * window of the EARLIEST position of THIS window (0: none; cleared after every window).  Both are maxima, so one native
+     * atomicMax serves each: the high half is raised with the low half carried along unchanged (it is stable while
+     * positions are being published), the low half while every high half is zero. */
+    alignas(16) uint32_t TT[1 << kEpHashLog];
+    alignas(16) uint8_t stage[kEpStage];
     uint32_t litJob[kEpMaxLitJobs][3];               /* {source position, output offset, length} */
     int warpLast[kEpWarps];                          /* chain scan: end of the last match selected in each warp, or -1 */
     uint32_t warpSum[kEpWarps];
@@ -64,23 +65,6 @@ struct EncParSmem {
     alignas(8) uint64_t mbar;
 };
 static_assert(sizeof(EncParSmem) <= (232448 - 2048) / 2, "two CTAs of the parallel compressor must fit one SM");
-
-/* atomicMax on a 16-bit shared-memory cell (CAS on the 32-bit word that holds it); the final value is the maximum of all
- * values offered, whatever the order: scheduling-independent */
-__device__ __forceinline__ void ep_atomic_max_u16(uint16_t* cell, uint32_t v)
-{
-    const uintptr_t u = reinterpret_cast<uintptr_t>(cell);
-    uint32_t* w = reinterpret_cast<uint32_t*>(u & ~uintptr_t(3));
-    const uint32_t sh = (uint32_t)(u & 2u) * 8u;
-    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(w);
-    for (;;) {
-        if (((cur >> sh) & 0xFFFFu) >= v) return;
-        const uint32_t nw = (cur & ~(0xFFFFu << sh)) | (v << sh);
-        const uint32_t old = atomicCAS(w, cur, nw);
-        if (old == cur) return;
-        cur = old;
-    }
-}
 
 __device__ __forceinline__ uint32_t ep_ld32(const uint8_t* base, uint32_t i)      /* unaligned 4 bytes at base + i (base 4-aligned) */
 {
@@ -116,10 +100,11 @@ struct EpBytes {
 __device__ __forceinline__ uint32_t ep_table_candidate(const EncParSmem& S, const uint8_t* src, int head, int p, int c0, uint32_t v)
 {
     const uint32_t h = ep_hash(v);
-    const uint32_t e = S.T2[h];
+    const uint32_t tt = S.TT[h];
+    const uint32_t e = tt >> 16;
     const int q = c0 + (0xFFFF - (int)e);                                          /* earliest position of this window with this hash */
     if (e && q < p && ep_ld32(src, (uint32_t)(head + q)) == v) return (uint32_t)q;
-    const uint32_t o = S.T[h];
+    const uint32_t o = tt & 0xFFFFu;
     if (o && ep_ld32(src, (uint32_t)head + o - 1u) == v) return o - 1u;
     return 0xFFFFFFFFu;
 }
@@ -181,10 +166,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
             for (uint32_t o = 0; o < loadBytes; o += 16384u) tma_load_1d(S.src + o, gsrc - head + o, min(16384u, loadBytes - o), &S.mbar);
             S.E = 0; S.O = 0; S.fail = 0; S.nLitJobs = 0;
         }
-        for (int k = tid; k < (1 << kEpHashLog) / 8; k += kEpThreads) {
-            reinterpret_cast<uint4*>(S.T)[k] = make_uint4(0, 0, 0, 0);
-            reinterpret_cast<uint4*>(S.T2)[k] = make_uint4(0, 0, 0, 0);
-        }
+        for (int k = tid; k < (1 << kEpHashLog) / 4; k += kEpThreads) reinterpret_cast<uint4*>(S.TT)[k] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         mbar_wait(&S.mbar, parity);
         parity ^= 1;
@@ -202,7 +184,10 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
             #pragma unroll
             for (int i = 0; i < kEpPer; i++)
                 if (i < cnt && (step == 1 || (p0 + i) % step == 0))
-                    ep_atomic_max_u16(&S.T2[ep_hash(by.val(i))], (uint32_t)(0xFFFF - (i0 + i)));
+                {
+                    uint32_t* cell = &S.TT[ep_hash(by.val(i))];
+                    atomicMax(cell, ((uint32_t)(0xFFFF - (i0 + i)) << 16) | (*cell & 0xFFFFu));
+                }
             __syncthreads();
             PHASE_MARK(0);                                     // find 1
             /* ---------------- find 2: which positions have a candidate ---------------- */
@@ -387,21 +372,27 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                     const uint32_t from = S.litJob[j][0], to = S.litJob[j][1], cntL = S.litJob[j][2];
                     for (uint32_t i = lane; i < cntL; i += 32) obase[to + i] = src[head + from + i];
                 }
-                /* ---------------- insert: this window's positions enter T ---------------- */
+                /* this window's "earliest position" halves are done with */
+                for (int k = tid; k < (1 << kEpHashLog) / 4; k += kEpThreads) {
+                    uint4 t = reinterpret_cast<uint4*>(S.TT)[k];
+                    t.x &= 0xFFFFu; t.y &= 0xFFFFu; t.z &= 0xFFFFu; t.w &= 0xFFFFu;
+                    reinterpret_cast<uint4*>(S.TT)[k] = t;
+                }
+                __syncthreads();
+                /* ---------------- insert: this window's positions enter the low halves ---------------- */
                 #pragma unroll
                 for (int i = 0; i < kEpPer; i++)
                     if (i < cnt && (step == 1 || (p0 + i) % step == 0))
-                        ep_atomic_max_u16(&S.T[ep_hash(by.val(i))], (uint32_t)(p0 + i) + 1u);
-                __syncthreads();
-                /* write the window out in aligned 16-byte pieces and hand the bytes back to T2, cleared */
+                        atomicMax(&S.TT[ep_hash(by.val(i))], (uint32_t)(p0 + i) + 1u);
+                /* write the window out in aligned 16-byte pieces */
                 {
                     const bool put = staged && !S.fail;
                     uint8_t* const gbase = dst + O0 - mis;                        /* 16-byte aligned; stage byte i belongs at gbase + i */
-                    for (uint32_t c = tid; c < (uint32_t)kEpStage / 16u; c += kEpThreads) {
+                    const uint32_t nChunk = put ? (mis + winTotal + 15u) / 16u : 0u;
+                    for (uint32_t c = tid; c < nChunk; c += kEpThreads) {
                         const uint4 v = reinterpret_cast<const uint4*>(S.stage)[c];
-                        reinterpret_cast<uint4*>(S.stage)[c] = make_uint4(0, 0, 0, 0);
                         const uint32_t lo = c * 16u;
-                        if (put && lo + 16u > mis && lo < mis + winTotal) {
+                        if (lo + 16u > mis) {
                             if (lo >= mis && lo + 16u <= mis + winTotal) *reinterpret_cast<uint4*>(gbase + lo) = v;
                             else {
                                 const uint32_t wv[4] = {v.x, v.y, v.z, v.w};

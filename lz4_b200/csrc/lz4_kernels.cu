@@ -150,16 +150,10 @@ __device__ __forceinline__ bool rows_eligible(int n, int cap, uint32_t nseq, uin
 }
 
 /* ---- scan, one THREAD per block: reads through the read-only data cache with L1 prefetch hints ---- */
-#ifndef LZ4K_SCAN_LANE_STRIDE
-#define LZ4K_SCAN_LANE_STRIDE 1
-#endif
+
 __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
 {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-#if LZ4K_SCAN_LANE_STRIDE > 1
-    if (b % LZ4K_SCAN_LANE_STRIDE) return;               /* experiment: fewer blocks per warp = fewer distinct paths per step */
-    b /= LZ4K_SCAN_LANE_STRIDE;
-#endif
     if (b >= a.nBlocks) return;
     const WsView w = ws_view(a);
     const uint8_t* src = a.src + a.srcOff[b];
@@ -172,9 +166,6 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
     const int r = scan_block(mem, n, cap, &ns, marks, w.markStride);
     a.outSize[b] = r;
     w.nSeq[b] = ns;
-#ifdef LZ4K_PF_LOAD
-    if ((mem.sink ^ mem.pend) == 0x9E3779B9u && ns == 0x7FFFFFFFu) w.nSeq[b] = 0;       /* keeps the experiment's loads alive */
-#endif
     if (r > 0 && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
 }
 
@@ -183,12 +174,9 @@ __global__ void __launch_bounds__(128) lz4_scan_kernel(lz4k_decode_args a)
  * Lists go to the scratch part of the workspace (2 x markStride words per block), the per-block records to shared memory. */
 constexpr int kSplitThreads = 128;
 constexpr int kSplitBlocksPerCta = kSplitThreads / kSsLanes;
-constexpr int64_t kSplitMaxBlocks = 8192;         /* largest batch the split scan is the default for */
+constexpr int64_t kSplitMaxBlocks = 16384;        /* largest batch the split scan is the default for */
 
-#ifndef LZ4K_SS_MINB
-#define LZ4K_SS_MINB 10
-#endif
-__global__ void __launch_bounds__(kSplitThreads, LZ4K_SS_MINB) lz4_scan_split_kernel(lz4k_decode_args a)
+__global__ void __launch_bounds__(kSplitThreads, 10) lz4_scan_split_kernel(lz4k_decode_args a)
 {
     __shared__ SsBlock sh[kSplitBlocksPerCta];
     const int lane = threadIdx.x % kSsLanes, slot = threadIdx.x / kSsLanes;
@@ -1116,9 +1104,9 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
          * one-thread scan, so it only pays for blocks far beyond 64 KB (lz4frame's 4 MB blocks: 150 000 dependent steps for one thread) */
         const bool par = scanImpl >= 0 ? scanImpl == 1 : (a->dstCapArr == nullptr && a->dstCap > 65536);
         /* blocks of 16..64 KB: kSsLanes merging lanes per block (smaller blocks have too few sequences to split).  Measured
-         * (profiles/README.md): faster than one thread per block while the batch leaves SMs idle (1.31 against 1.85 ms for
-         * 8192 blocks), slower once the one-thread scan fills them (7.4 against 2.7 ms for 65536 blocks: four times the
-         * threads, each with its own cache lines in flight, overflow L1) */
+         * (profiles/README.md): faster than one thread per block while the batch is small (1.18 against 2.30 ms for
+         * 8192 blocks, 1.56 against 2.31 ms for 16384), slower beyond (3.07 against 2.37 ms for 32768, 7.4 against 2.7 ms
+         * for 65536: the one-thread scan's time hardly grows with the batch, the split scan's does) */
         const bool split = scanImpl >= 0 ? scanImpl == 2
                                          : (a->dstCapArr == nullptr && a->dstCap >= 16384 && a->dstCap <= 65536 && a->nBlocks <= kSplitMaxBlocks);
         if (split && !par) {
@@ -1130,7 +1118,7 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
             lz4_scan_par_kernel<<<(unsigned)grid, kScanLanes, sizeof(ScanParSmem), s>>>(*a);
         } else {
             const int threads = 128;
-            const int64_t grid = (a->nBlocks * LZ4K_SCAN_LANE_STRIDE + threads - 1) / threads;
+            const int64_t grid = (a->nBlocks + threads - 1) / threads;
             lz4_scan_kernel<<<(unsigned)grid, threads, 0, s>>>(*a);
         }
         g_launches++;

@@ -36,15 +36,6 @@ static inline uint32_t sc_funnel_r_host(uint32_t lo, uint32_t hi, uint32_t s)
 #define SC_PREFETCH_L1(p) ((void)(p))
 #endif
 
-/* stores of marks / scratch lists and reads of scratch lists: experiment LZ4K_ST_CG keeps them out of L1 (cache-global) */
-#if defined(__CUDACC__) && defined(LZ4K_ST_CG)
-#define SC_ST(p, v) __stcg((p), (v))
-#define SC_LD_SCRATCH(p) __ldcg(p)
-#else
-#define SC_ST(p, v) (*(p) = (v))
-#define SC_LD_SCRATCH(p) (*(p))
-#endif
-
 #ifndef LZ4_SCAN_CORE_CONSTANTS
 constexpr int kMinMatch = 4;
 constexpr int kLastLiterals = 5;
@@ -60,13 +51,6 @@ constexpr int kMfLimit = 12;
  * and dropped: 2.8 - 6.8 ms against 2.6 ms for the plain loads, profiles/README.md).
  * ------------------------------------------------------------------------------------------- */
 constexpr int kMemAhead = 32;
-/* L1 prefetch of the walk: one hint per 2^LZ4K_PF_STEP_LOG input bytes, LZ4K_PF_DIST bytes ahead */
-#ifndef LZ4K_PF_STEP_LOG
-#define LZ4K_PF_STEP_LOG 7
-#endif
-#ifndef LZ4K_PF_DIST
-#define LZ4K_PF_DIST 128
-#endif              /* bytes that ensure(i) makes readable: [i, i + kMemAhead) */
 
 template <bool G> SC_FN uint32_t ldb(const uint8_t* p) { return G ? (uint32_t)SC_LDG(p) : (uint32_t)*p; }
 template <bool G> SC_FN uint32_t ldw(const uint32_t* p) { return G ? SC_LDG(p) : *p; }
@@ -91,16 +75,7 @@ template <bool G> struct MemPtr {
     SC_MFN uint32_t u32(int64_t i) const { return ld32u<G>(p + i); }
     SC_MFN void ensure(int64_t) const { }
     SC_MFN void tick(int64_t) const { }
-#if defined(LZ4K_PF_LOAD) && defined(__CUDACC__)
-    /* experiment: the hint is a real load whose value is folded into `sink` one hint later */
-    mutable uint32_t pend = 0, sink = 0;
-    SC_MFN void prefetch(int64_t i) const
-    {
-        if (G) { sink ^= pend; pend = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p + i) & ~uintptr_t(3))); }
-    }
-#else
     SC_MFN void prefetch(int64_t i) const { if (G) SC_PREFETCH_L1(p + i); }
-#endif
     static constexpr bool kPrefetch = G;
 };
 
@@ -135,7 +110,7 @@ constexpr int kMaxSeqFast = 8192;              // most sequences a block of the 
 /* `markCap` = number of mark slots the caller reserved for this block (<= kMaxSeqFast); a block that can be
  * expanded from shared memory has at most capacity/4 + 1 sequences (every sequence but the last makes >= 4 bytes) */
 #define MARK_COMMIT(tokpos, matchpos)                                                           \
-    do { if (marks && nseq < markCap) SC_ST(&marks[nseq], (uint32_t)(tokpos) | ((uint32_t)(matchpos) << 16)); } while (0)
+    do { if (marks && nseq < markCap) marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(matchpos) << 16); } while (0)
 
 /* where the walk of one block stands between its two loops */
 struct ScanState {
@@ -164,9 +139,9 @@ template <class M> SC_FN bool scan_front(M& mem, int nIn, int capIn, ScanState& 
      * (literal runs < 525 bytes, matches < 529); longer ones go round the reference's loops, which are skipped
      * (condition false for every lane) otherwise.  The exits are collected and taken once, in the reference's order. */
     while (fip <= nI - 26) {
-        if (M::kPrefetch && fip >= nextEvt) {                      // L1 prefetch hint
-            if (fip + LZ4K_PF_DIST < nI) mem.prefetch(fip + LZ4K_PF_DIST);
-            nextEvt = ((fip >> LZ4K_PF_STEP_LOG) + 1) << LZ4K_PF_STEP_LOG;
+        if (M::kPrefetch && fip >= nextEvt) {                      // L1 prefetch hint, once per 128 input bytes (finer / farther / real loads: no change, profiles/README.md)
+            if (fip + 128 < nI) mem.prefetch(fip + 128);
+            nextEvt = ((fip >> 7) + 1) << 7;
         }
         mem.tick(fip);
         mem.ensure(fip);                                           // [fip, fip + kMemAhead) is readable: token, short literals, offset

@@ -117,8 +117,8 @@ SC_FN int ss_seg_start(int lane, int nI)
 SC_FN bool ss_push(SsPub& me, uint32_t* A, uint32_t* B, uint32_t R, int tok, uint32_t off16, uint32_t opn)
 {
     if (me.cnt >= R) { me.state = SS_FULL; return false; }
-    SC_ST(&A[me.cnt], opn);
-    SC_ST(&B[me.cnt], (uint32_t)tok | (off16 << 16));
+    A[me.cnt] = opn;
+    B[me.cnt] = (uint32_t)tok | (off16 << 16);
     me.cnt++;
     return true;
 }
@@ -135,8 +135,8 @@ SC_FN void ss_p1(int lane, SsBlock& S, M& mem, int nI, uint32_t* A, uint32_t* B,
     int nextEvt = 0;
     while (fip < segEnd) {
         if (M::kPrefetch && fip >= nextEvt) {
-            if (fip + LZ4K_PF_DIST < nI) mem.prefetch(fip + LZ4K_PF_DIST);
-            nextEvt = ((fip >> LZ4K_PF_STEP_LOG) + 1) << LZ4K_PF_STEP_LOG;
+            if (fip + 128 < nI) mem.prefetch(fip + 128);
+            nextEvt = ((fip >> 7) + 1) << 7;
         }
         int ipn, lit, mlen; uint32_t off16;
         if (!ss_step(mem, nI, fip, ipn, lit, mlen, off16)) { me.state = SS_STOP; break; }
@@ -161,7 +161,7 @@ SC_FN void ss_p2(int lane, SsBlock& S, M& mem, int nI, uint32_t* A, uint32_t* B,
     for (;;) {
         /* the next token of lane t's P1 chain at or after... : its committed entries, then the position it stopped at */
         const SsPub& T = S.lane[t];
-        const int tk = (cur < T.cntP1) ? (int)(SC_LD_SCRATCH(&scratchB(t)[cur]) & 0xFFFFu) : T.fipP1;
+        const int tk = (cur < T.cntP1) ? (int)(scratchB(t)[cur] & 0xFFFFu) : T.fipP1;
         if (fip > tk) {
             if (cur < T.cntP1) { cur++; continue; }
             if (t + 1 < kSsLanes) { t++; cur = 0; continue; }          /* lane t never met the chain: void */
@@ -199,7 +199,7 @@ SC_FN void ss_p3(SsBlock& S, ListA scratchA)
         first = L.mergeIdx;
         /* lane T's relative match start of the same sequence: its entry, or -- when it committed nothing from there on --
          * what it computed for its own merge at this very token */
-        const uint32_t rel = (T.cnt > first) ? SC_LD_SCRATCH(&scratchA(L.target)[first]) : T.mergeOpn;
+        const uint32_t rel = (T.cnt > first) ? scratchA(L.target)[first] : T.mergeOpn;
         base = trueOpn - rel;
         j = L.target;
     }
@@ -214,10 +214,10 @@ SC_FN void ss_p4(int lane, SsBlock& S, int capI, const uint32_t* A, const uint32
     if (!me.inChain) return;
     for (uint32_t k = me.first; k < me.cnt; k++) {
         const uint32_t g = me.place + (k - me.first);
-        const uint32_t opn = SC_LD_SCRATCH(&A[k]) + me.base, tb = SC_LD_SCRATCH(&B[k]);
+        const uint32_t opn = A[k] + me.base, tb = B[k];
         if ((tb >> 16) > opn && errIdx == 0xFFFFFFFFu) errIdx = g;                               /* lz4.c:2161 */
         if ((int64_t)opn >= (int64_t)capI - 64 && capIdx == 0xFFFFFFFFu) { capIdx = g; capOpn = opn; }
-        if (marks && g < markCap) SC_ST(&marks[g], (tb & 0xFFFFu) | (opn << 16));
+        if (marks && g < markCap) marks[g] = (tb & 0xFFFFu) | (opn << 16);
     }
 }
 
@@ -230,10 +230,10 @@ SC_FN int ss_p5(SsBlock& S, M& mem, int nIn, int capIn, uint32_t* nSeqOut, uint3
     const int fipEnd = E.fip;
     const uint32_t fopEnd = E.fop + E.base;
     /* token position / output start of front-loop sequence g (g <= K; g == K: where the walk ended) */
-    auto tokOf = [&](uint32_t g) -> int { return g < K ? (int)(SC_LD_SCRATCH(&marks[g]) & 0xFFFFu) : fipEnd; };
+    auto tokOf = [&](uint32_t g) -> int { return g < K ? (int)(marks[g] & 0xFFFFu) : fipEnd; };
     auto startOf = [&](uint32_t g) -> uint32_t {
         if (g >= K) return fopEnd;
-        uint32_t opn = (g == S.capIdx) ? S.capOpn : (SC_LD_SCRATCH(&marks[g]) >> 16);      /* (before capIdx every match start is below the capacity: 16 bits) */
+        uint32_t opn = (g == S.capIdx) ? S.capOpn : (marks[g] >> 16);      /* (before capIdx every match start is below the capacity: 16 bits) */
         return opn - (uint32_t)ss_lit_at(mem, tokOf(g));
     };
     /* capacity rule (lz4.c:2137/2142; lz4.c:2104 implies it): the front loop stops at the first sequence that ENDS at or past
