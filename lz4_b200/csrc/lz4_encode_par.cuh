@@ -45,8 +45,6 @@ constexpr int kEpWin = kEpThreads * kEpPer;          /* 8192 positions per windo
 constexpr int kEpHashLog = 13;
 constexpr int kEpMaxSel = kEpPer / 4;                /* matches are >= 4 long: at most 4 selections per lane */
 constexpr int kEpSolo = 32;                          /* bytes a lane compares alone (> kEpPer: a longer match ends the lane's walk) */
-constexpr int kEpInlineLits = 32;                    /* literal runs up to this length are copied by the emitting thread */
-constexpr int kEpMaxLitJobs = 256;                   /* (at most 8192/33 longer literal runs end in a window) */
 constexpr int kEpStage = kEpWin + 512;               /* a window's output is assembled here when it fits (it does unless literals of earlier windows come with it) */
 
 struct EncParSmem {
@@ -58,10 +56,11 @@ struct EncParSmem {
      * positions are being published), the low half while every high half is zero. */
     alignas(16) uint32_t TT[1 << kEpHashLog];
     alignas(16) uint8_t stage[kEpStage];
-    uint32_t litJob[kEpMaxLitJobs][3];               /* {source position, output offset, length} */
+    uint32_t carry[3];                               /* literals of EARLIER windows that the window's first sequence carries: {source position, output offset, length} */
+    int warpFirst[kEpWarps][2];                      /* emit: {start, output offset - position of its literals (relative to the warp's output)} of the warp's first sequence */
     int warpLast[kEpWarps];                          /* chain scan: end of the last match selected in each warp, or -1 */
     uint32_t warpSum[kEpWarps];
-    uint32_t nLitJobs, E, O, fail;
+    uint32_t E, O, fail;
     alignas(8) uint64_t mbar;
 };
 static_assert(sizeof(EncParSmem) <= (232448 - 2048) / 2, "two CTAs of the parallel compressor must fit one SM");
@@ -96,26 +95,25 @@ struct EpBytes {
     }
 };
 
-/* candidate of position p (window first position c0), 0xFFFFFFFF if none; v = the 4 bytes at p */
-__device__ __forceinline__ uint32_t ep_table_candidate(const EncParSmem& S, const uint8_t* src, int head, int p, int c0, uint32_t v)
+/* Where a position's candidate comes from, 4 bits per position (0: none): 1..4 = p - d (short-period rule), kEpKindWin = this
+ * window's earliest position with the hash, kEpKindOld = the earlier windows' latest.  find 2 verifies and records the kind;
+ * select turns the kind of the few SELECTED positions back into a position (the table does not change in between). */
+constexpr uint32_t kEpKindWin = 5, kEpKindOld = 6;
+__device__ __forceinline__ uint32_t ep_table_kind(const EncParSmem& S, const uint8_t* src, int head, int p, int c0, uint32_t v)
 {
-    const uint32_t h = ep_hash(v);
-    const uint32_t tt = S.TT[h];
+    const uint32_t tt = S.TT[ep_hash(v)];
     const uint32_t e = tt >> 16;
     const int q = c0 + (0xFFFF - (int)e);                                          /* earliest position of this window with this hash */
-    if (e && q < p && ep_ld32(src, (uint32_t)(head + q)) == v) return (uint32_t)q;
+    if (e && q < p && ep_ld32(src, (uint32_t)(head + q)) == v) return kEpKindWin;
     const uint32_t o = tt & 0xFFFFu;
-    if (o && ep_ld32(src, (uint32_t)head + o - 1u) == v) return o - 1u;
-    return 0xFFFFFFFFu;
+    if (o && ep_ld32(src, (uint32_t)head + o - 1u) == v) return kEpKindOld;
+    return 0u;
 }
-/* the same incl. the short-period rule (5 bytes repeat at distance d <= 4), from memory: for the few SELECTED positions */
-__device__ __forceinline__ uint32_t ep_candidate(const EncParSmem& S, const uint8_t* src, int head, int p, int c0)
+__device__ __forceinline__ uint32_t ep_candidate_of_kind(const EncParSmem& S, const uint8_t* src, int head, int p, int c0, uint32_t kind)
 {
-    const uint32_t v = ep_ld32(src, (uint32_t)(head + p));
-    #pragma unroll
-    for (int d = 1; d <= 4; d++)
-        if (p >= d && ep_ld32(src, (uint32_t)(head + p - d)) == v && src[head + p + 4] == src[head + p + 4 - d]) return (uint32_t)(p - d);
-    return ep_table_candidate(S, src, head, p, c0, v);
+    if (kind <= 4u) return (uint32_t)p - kind;
+    const uint32_t tt = S.TT[ep_hash(ep_ld32(src, (uint32_t)(head + p)))];
+    return kind == kEpKindWin ? (uint32_t)(c0 + 0xFFFF) - (tt >> 16) : (tt & 0xFFFFu) - 1u;
 }
 
 /* length of the match (p, c), both block positions, at most `limit` (>= 4): two word streams, 4 bytes per step */
@@ -164,7 +162,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
         if (tid == 0) {
             mbar_expect_tx(&S.mbar, loadBytes);
             for (uint32_t o = 0; o < loadBytes; o += 16384u) tma_load_1d(S.src + o, gsrc - head + o, min(16384u, loadBytes - o), &S.mbar);
-            S.E = 0; S.O = 0; S.fail = 0; S.nLitJobs = 0;
+            S.E = 0; S.O = 0; S.fail = 0; S.carry[2] = 0;
         }
         for (int k = tid; k < (1 << kEpHashLog) / 4; k += kEpThreads) reinterpret_cast<uint4*>(S.TT)[k] = make_uint4(0, 0, 0, 0);
         __syncthreads();
@@ -192,17 +190,18 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
             PHASE_MARK(0);                                     // find 1
             /* ---------------- find 2: which positions have a candidate ---------------- */
             uint32_t has = 0;
+            uint64_t kinds = 0;
             #pragma unroll
             for (int i = 0; i < kEpPer; i++) {
                 if (i < cnt && (step == 1 || (p0 + i) % step == 0)) {
                     const int p = p0 + i;
                     const uint32_t v = by.val(i);
-                    bool found = false;
+                    uint32_t kind = 0;
                     #pragma unroll
                     for (int d = 1; d <= 4; d++)                     /* a run of period d <= 4: the 5 bytes at p repeat at p - d */
-                        if (!found && p >= d && by.val(i - d) == v && src[head + p + 4] == src[head + p + 4 - d]) found = true;
-                    if (!found) found = ep_table_candidate(S, src, head, p, c0, v) != 0xFFFFFFFFu;
-                    if (found) has |= 1u << i;
+                        if (!kind && p >= d && by.val(i - d) == v && src[head + p + 4] == src[head + p + 4 - d]) kind = (uint32_t)d;
+                    if (!kind) kind = ep_table_kind(S, src, head, p, c0, v);
+                    if (kind) { has |= 1u << i; kinds |= (uint64_t)kind << (4 * i); }
                 }
             }
             PHASE_MARK(1);                                     // find 2
@@ -231,7 +230,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                             if (p == cacheP) { c = cacheC; L = cacheL; }
                             else {
                                 const int limit = matchlimit - p;
-                                c = ep_candidate(S, src, head, p, c0);
+                                c = ep_candidate_of_kind(S, src, head, p, c0, (uint32_t)(kinds >> (4 * rel)) & 15u);
                                 L = ep_extend(src, head, p, c, min(limit, kEpSolo));
                                 if (L >= kEpSolo && L < limit) pendK = k;
                             }
@@ -314,9 +313,14 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                 S.E = (uint32_t)(last < 0 ? Ein : last);
             }
             PHASE_MARK(4);                                     // select
-            /* ---------------- emit ---------------- */
+            /* ---------------- emit ----------------
+             * Every selection's sequence header (token, length bytes, offset, length bytes) is written by its lane; the LITERALS are
+             * copied position-parallel: every lane stores those of its own 16 positions that are literals, at (position + D) where D
+             * is constant per literal run -- the run belongs to the next sequence at or after the position, which a suffix scan
+             * ("first sequence to the right") hands to the lanes that select nothing.  Only the literals that the window's first
+             * sequence brings along from EARLIER windows have no owner lane: the whole CTA copies them. */
             {
-                uint32_t size = 0;
+                uint32_t size = 0, hdr0 = 0;
                 #pragma unroll
                 for (int k = 0; k < kEpMaxSel; k++) {
                     if (k < nSel) {
@@ -325,52 +329,96 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                         uint32_t c = sCand[k];
                         while (p > A && c > 0u && src[head + p - 1] == src[head + c - 1u]) { p--; c--; L++; }      /* lz4.c:1107-1109 */
                         sPos[k] = p; sLen[k] = L; sCand[k] = c;
-                        size += 1u + ep_runlen_bytes((uint32_t)(p - A)) + (uint32_t)(p - A) + 2u + ep_runlen_bytes((uint32_t)(L - kMinMatch));
+                        const uint32_t h = 1u + ep_runlen_bytes((uint32_t)(p - A));
+                        if (k == 0) hdr0 = h;
+                        size += h + (uint32_t)(p - A) + 2u + ep_runlen_bytes((uint32_t)(L - kMinMatch));
                     }
                 }
                 uint32_t incl = size;
                 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += y; }
+                /* first sequence at or after this lane: {start, D relative to the warp's first output byte} */
+                int nStart = nSel ? sPos[0] : -1;
+                int nD = nSel ? (int)(incl - size + hdr0) - sLit[0] : 0;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int y = __shfl_down_sync(kFull, nStart, d), z = __shfl_down_sync(kFull, nD, d);
+                    if (lane + d < 32 && nStart < 0) { nStart = y; nD = z; }
+                }
                 if (lane == 31) S.warpSum[warp] = incl;
+                if (lane == 0) { S.warpFirst[warp][0] = nStart; S.warpFirst[warp][1] = nD; }
+                int xStart = __shfl_down_sync(kFull, nStart, 1), xD = __shfl_down_sync(kFull, nD, 1);     /* ... strictly after this lane */
+                if (lane == 31) xStart = -1;
                 __syncthreads();
                 const uint32_t O0 = S.O;
                 uint32_t base = O0, winTotal = 0;
                 for (int q = 0; q < kEpWarps; q++) { const uint32_t x = S.warpSum[q]; winTotal += x; if (q < warp) base += x; }
+                if (xStart >= 0) xD += (int)base;
+                else {
+                    uint32_t bq = base + S.warpSum[warp];
+                    for (int q = warp + 1; q < kEpWarps; q++) {
+                        const int st = S.warpFirst[q][0];
+                        if (st >= 0) { xStart = st; xD = S.warpFirst[q][1] + (int)bq; break; }
+                        bq += S.warpSum[q];
+                    }
+                }
                 /* (a window's output can exceed its 8192 positions: its first sequence carries the literals of earlier windows) */
                 const bool staged = winTotal + 16u <= (uint32_t)kEpStage;
                 const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst + O0) & 15u);   /* stage keeps the 16-byte phase of the destination */
                 uint8_t* const obase = staged ? S.stage + mis - O0 : dst;       /* output offset o lives at obase + o */
+                const int64_t lim = staged ? (int64_t)1 << 40 : cap;            /* direct stores must stay below the capacity */
                 int64_t o = (int64_t)base + incl - size;
-                if (size && o + size > cap) S.fail = 1;
-                else {
+                uint32_t lm[kEpMaxSel + 1];                                      /* literal positions of this lane, per run: bit i = position p0 + i */
+                int lD[kEpMaxSel + 1];
+                auto range = [&](int from, int to) -> uint32_t {                 /* bits of the own positions in [from, to) */
+                    const int lo = min(max(from - p0, 0), kEpPer), hi = min(max(to - p0, 0), kEpPer);
+                    return hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+                };
+                const bool fits = o + size <= cap;
+                if (size && !fits) S.fail = 1;
+                #pragma unroll
+                for (int k = 0; k < kEpMaxSel; k++) {
+                    lm[k] = 0; lD[k] = 0;
+                    if (k < nSel && fits) {
+                        uint8_t* d = obase + o;
+                        const int ll = sPos[k] - sLit[k];
+                        const uint32_t ml = (uint32_t)(sLen[k] - kMinMatch);
+                        *d++ = (uint8_t)((min((uint32_t)ll, 15u) << 4) | min(ml, 15u));
+                        if (ll >= 15) { uint32_t r = (uint32_t)ll - 15u; while (r >= 255u) { *d++ = 255; r -= 255u; } *d++ = (uint8_t)r; }
+                        const uint32_t litDst = (uint32_t)(d - obase);
+                        lD[k] = (int)litDst - sLit[k];
+                        lm[k] = range(sLit[k], sPos[k]);
+                        if (sLit[k] < c0) { S.carry[0] = (uint32_t)sLit[k]; S.carry[1] = litDst; S.carry[2] = (uint32_t)(min(c0, sPos[k]) - sLit[k]); }
+                        d += ll;
+                        const uint32_t off = (uint32_t)sPos[k] - sCand[k];
+                        *d++ = (uint8_t)off; *d++ = (uint8_t)(off >> 8);
+                        if (ml >= 15u) { uint32_t r = ml - 15u; while (r >= 255u) { *d++ = 255; r -= 255u; } *d++ = (uint8_t)r; }
+                        o = d - obase;
+                    }
+                }
+                /* the positions after this lane's last match (or after the match that covers its start) up to the next sequence */
+                lm[kEpMaxSel] = xStart >= 0 ? range(nSel ? exitE : eCur, xStart) : 0u;
+                lD[kEpMaxSel] = xD;
+                {
+                    uint32_t any = lm[kEpMaxSel];
                     #pragma unroll
-                    for (int k = 0; k < kEpMaxSel; k++) {
-                        if (k < nSel) {
-                            uint8_t* d = obase + o;
-                            const int ll = sPos[k] - sLit[k];
-                            const uint32_t ml = (uint32_t)(sLen[k] - kMinMatch);
-                            *d++ = (uint8_t)((min((uint32_t)ll, 15u) << 4) | min(ml, 15u));
-                            if (ll >= 15) { uint32_t r = (uint32_t)ll - 15u; while (r >= 255u) { *d++ = 255; r -= 255u; } *d++ = (uint8_t)r; }
-                            if (ll <= kEpInlineLits) {
-                                for (int i = 0; i < ll; i++) d[i] = src[head + sLit[k] + i];
-                            } else {
-                                const uint32_t j = atomicAdd(&S.nLitJobs, 1u);
-                                S.litJob[j][0] = (uint32_t)sLit[k]; S.litJob[j][1] = (uint32_t)(d - obase); S.litJob[j][2] = (uint32_t)ll;
-                            }
-                            d += ll;
-                            const uint32_t off = (uint32_t)sPos[k] - sCand[k];
-                            *d++ = (uint8_t)off; *d++ = (uint8_t)(off >> 8);
-                            if (ml >= 15u) { uint32_t r = ml - 15u; while (r >= 255u) { *d++ = 255; r -= 255u; } *d++ = (uint8_t)r; }
-                            o = d - obase;
+                    for (int k = 0; k < kEpMaxSel; k++) any |= lm[k];
+                    #pragma unroll
+                    for (int i = 0; i < kEpPer; i++) {
+                        if ((any >> i) & 1u) {
+                            int D = lD[kEpMaxSel];
+                            #pragma unroll
+                            for (int k = kEpMaxSel - 1; k >= 0; k--) if ((lm[k] >> i) & 1u) D = lD[k];
+                            const int64_t at = (int64_t)(p0 + i) + D;
+                            if (at < lim) obase[at] = (uint8_t)by.val(i);
                         }
                     }
                 }
                 __syncthreads();
                 if (tid == 0) S.O = O0 + winTotal;
-                const uint32_t nLit = S.nLitJobs;
-                for (uint32_t j = warp; j < nLit; j += kEpWarps) {
-                    const uint32_t from = S.litJob[j][0], to = S.litJob[j][1], cntL = S.litJob[j][2];
-                    for (uint32_t i = lane; i < cntL; i += 32) obase[to + i] = src[head + from + i];
+                {
+                    const uint32_t from = S.carry[0], to = S.carry[1], cntL = S.carry[2];
+                    for (uint32_t i = tid; i < cntL; i += kEpThreads) if ((int64_t)to + i < lim) obase[to + i] = src[head + from + i];
                 }
                 /* this window's "earliest position" halves are done with */
                 for (int k = tid; k < (1 << kEpHashLog) / 4; k += kEpThreads) {
@@ -403,7 +451,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                         }
                     }
                 }
-                if (tid == 0) S.nLitJobs = 0;
+                if (tid == 0) S.carry[2] = 0;
                 __syncthreads();
                 PHASE_MARK(5);                                 // emit + insert
             }
