@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                     uint32_t kind = 0;
                     #pragma unroll
                     for (int d = 1; d <= 4; d++)                     /* a run of period d <= 4: the 5 bytes at p repeat at p - d */
-                        if (!kind && p >= d && by.val(i - d) == v && src[head + p + 4] == src[head + p + 4 - d]) kind = (uint32_t)d;
+                        if (!kind && p >= d && by.val(i - d) == v && ((by.val(i + 1) ^ by.val(i + 1 - d)) >> 24) == 0u) kind = (uint32_t)d;
                     if (!kind) kind = ep_table_kind(S, src, head, p, c0, v);
                     if (kind) { has |= 1u << i; kinds |= (uint64_t)kind << (4 * i); }
                 }
@@ -279,27 +279,51 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
 #ifdef LZ4K_PHASE_TIMING
             unsigned statRounds = 0, statWalks = 1;
 #endif
+            /* Two levels of rounds.  Inside a warp the chain is settled with shuffles alone (no CTA barrier): given the position the
+             * chain enters the WARP at, every lane takes the end of the last match selected before it and walks again if its search
+             * would start elsewhere.  Across warps one barrier per round hands every warp the end of the last match selected in the
+             * warps before it; a warp whose entry moved settles again.  The chain usually re-synchronises within a warp's 512
+             * positions, so two CTA rounds are the rule. */
+            int warpEntry = Ein;
             for (;;) {
-                /* end of the last match selected at or before this lane (lanes that select nothing pass the chain through) */
-                int val = nSel ? exitE : -1;
-                #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(kFull, val, d); if (lane >= d && val < 0) val = y; }
+                int val;
+                for (;;) {
+                    /* end of the last match selected at or before this lane (lanes that select nothing pass the chain through) */
+                    val = nSel ? exitE : -1;
+                    #pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(kFull, val, d); if (lane >= d && val < 0) val = y; }
+                    int prev = __shfl_up_sync(kFull, val, 1);            /* ... at or before the previous lane */
+                    if (lane == 0) prev = -1;
+                    const int eNew = prev < 0 ? warpEntry : prev;
+                    const bool need = max(eNew - p0, 0) != max(eCur - p0, 0);      /* the search would start elsewhere */
+                    eCur = eNew;
+                    if (!__any_sync(kFull, need)) break;
+#ifdef LZ4K_PHASE_TIMING
+                    statWalks += need ? 1u : 0u;
+#endif
+                    walk(need, eNew);
+                }
                 if (lane == 31) S.warpLast[warp] = val;
                 __syncthreads();
                 int carry = -1;                                         /* ... in the warps before this one */
                 for (int q = warp - 1; q >= 0; q--) { const int x = S.warpLast[q]; if (x >= 0) { carry = x; break; } }
-                int prev = __shfl_up_sync(kFull, val, 1);                /* ... at or before the previous lane */
-                if (lane == 0) prev = -1;
-                if (prev < 0) prev = carry;
-                const int eNew = prev < 0 ? Ein : prev;
-                const bool need = max(eNew - p0, 0) != max(eCur - p0, 0);          /* the search would start elsewhere */
-                eCur = eNew;
-                const int anyNeed = __syncthreads_or(need ? 1 : 0);
-                if (!anyNeed) break;
+                const int entry = carry < 0 ? Ein : carry;
+                const int w0 = c0 + kEpPer * 32 * warp;                  /* the warp's first position */
+                const bool moved = max(entry - w0, 0) != max(warpEntry - w0, 0);
+                warpEntry = entry;
+                if (!__syncthreads_or(moved ? 1 : 0)) break;
 #ifdef LZ4K_PHASE_TIMING
-                statRounds++; statWalks += need ? 1u : 0u;
+                statRounds++;
 #endif
-                walk(need, eNew);
+            }
+            {
+                /* the true position the chain enters this lane at (an entry below the lane's first position was not propagated) */
+                int val = nSel ? exitE : -1;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(kFull, val, d); if (lane >= d && val < 0) val = y; }
+                int prev = __shfl_up_sync(kFull, val, 1);
+                if (lane == 0) prev = -1;
+                eCur = prev < 0 ? warpEntry : prev;
             }
 #ifdef LZ4K_PHASE_TIMING
             if (tid == 0) atomicAdd(&g_loopStats[0], (unsigned long long)statRounds);
