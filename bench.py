@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--chunks", type=int, default=4, help="N > 1: pieces of a rank's shard whose exchange overlaps the decode of the next piece")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = copy-engine pushes into the peers' frames (CUDA IPC over NVLink), 'nccl' = grouped NCCL send/recv")
     return ap.parse_args()
 
 
@@ -353,12 +355,14 @@ def run_ours(args):
         batch.decompress_blocks(packed, offs[lo:hi], csizes[lo:hi], BLOCK, out=out[lo * BLOCK:hi * BLOCK],
                                 out_sizes=rets[lo:hi], workspace=ws, phases=phases)
 
+    peer = ldist.PeerFrame(full) if world > 1 and args.exchange == "peer" else None
+
     def step():
         """one pass of the hot path over this rank's batch; N > 1: + the exchange of the decoded shards, overlapped"""
         if world == 1:
             decode()
         else:
-            ldist.decode_and_allgather(full, n_blocks, BLOCK, decode, n_chunks=args.chunks)
+            ldist.decode_and_allgather(full, n_blocks, BLOCK, decode, n_chunks=args.chunks, peer=peer)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -539,8 +543,11 @@ def run_ours(args):
                               "clocks": par_clocks},
     }
     if world > 1:
-        line["multi_gpu"] = {"value_includes": "decode + exchange of the decoded shards (grouped NCCL send/recv per chunk, "
-                                               "%d chunks, exchange of chunk k overlaps the decode of chunk k+1)" % args.chunks,
+        how = ("copy-engine pushes into the peers' frames over NVLink peer memory (CUDA IPC), one stream per peer"
+               if args.exchange == "peer" else "grouped NCCL send/recv per chunk")
+        line["multi_gpu"] = {"value_includes": "decode + exchange of the decoded shards (%s; %d chunks, exchange of chunk k "
+                                               "overlaps the decode of chunk k+1)" % (how, args.chunks),
+                             "exchange": args.exchange,
                              "per_rank_ms_per_step": per_rank_ms,
                              "codec_only": {"ms_per_step_max_over_ranks": round(codec_ms_max, 4),
                                             "GBps": round(world * total / (codec_ms_max * 1e-3) / GB, 3)},

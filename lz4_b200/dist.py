@@ -53,7 +53,52 @@ def chunk_ranges(n_units, n_chunks):
     return out
 
 
-def decode_and_allgather(full, blocks_per_rank, block_size, decode_chunk, n_chunks=4, group=None):
+class PeerFrame:
+    """Every rank's copy of the frame, mapped into every other rank's address space (CUDA IPC; NVLink peer memory).
+
+    With it the exchange of a decoded chunk is R-1 device-to-device copies issued by the rank that decoded it, straight
+    into the chunk's final place in each peer's frame.  The copies run on the GPU's copy engines, one stream per peer:
+    they take no SM away from the codec's persistent kernels -- NCCL's send/recv kernels do, which made the overlapped
+    NCCL exchange SLOWER than the serial one (2 GPUs, 4 GiB per rank: 19.5 ms with 4 chunks, 16.5 ms with one;
+    profiles/experiments_r02.txt).  Collective construction: every rank of `group` must call it with its own `full`."""
+
+    def __init__(self, full, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.full = full
+        handles = [None] * self.world
+        dist.all_gather_object(handles, reduce_tensor(full), group=group)
+        self.peers = [None] * self.world                       # peers[r] = rank r's frame, writable from here
+        for r, (fn, fargs) in enumerate(handles):
+            if r != self.rank:
+                self.peers[r] = fn(*fargs)
+        self.streams = [torch.cuda.Stream(device=full.device) for _ in range(self.world - 1)]
+        self.token = torch.zeros(1, dtype=torch.int32, device=full.device)
+        dist.barrier(group)                                    # nobody pushes before everybody has mapped
+
+    def push(self, lo, hi):
+        """Enqueue the copy of full[lo:hi] (this rank's freshly decoded bytes, ordered after the current stream's work so
+        far) into the same place of every peer's frame."""
+        ev = torch.cuda.Event()
+        ev.record()
+        for i in range(self.world - 1):
+            r = (self.rank + 1 + i) % self.world               # staggered: no hot receiver
+            st = self.streams[i]
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                self.peers[r][lo:hi].copy_(self.full[lo:hi], non_blocking=True)
+
+    def finish(self):
+        """Order the current stream after this rank's pushes and after every peer's pushes into this rank."""
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            cur.wait_stream(st)
+        dist.all_reduce(self.token, group=self.group)          # a rank contributes only after its own pushes (stream order)
+
+
+def decode_and_allgather(full, blocks_per_rank, block_size, decode_chunk, n_chunks=4, group=None, peer=None):
     """Decode this rank's shard chunk by chunk and exchange every chunk as soon as it is decoded, so that the
     exchange of chunk k runs while chunk k+1 is being decoded (the ordered-writer role of lz4io.c:594-635, spread
     over the ranks: afterwards every rank holds the whole decoded frame).
@@ -65,6 +110,8 @@ def decode_and_allgather(full, blocks_per_rank, block_size, decode_chunk, n_chun
     straight into their final place in `full` -- no staging buffer and no re-ordering copy, which a chunk-wise
     ncclAllGather (contiguous output per call) would need.  The collective stream waits for the decode of chunk k
     through the event torch.distributed records at issue time; the codec stream carries on with chunk k+1.
+    With `peer` (a PeerFrame over `full`) the exchange of a chunk is R-1 copy-engine copies into the peers' frames
+    instead (no SM use; see PeerFrame).
     Returns the list of outstanding works (already waited for: the current stream is ordered after them)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -75,6 +122,9 @@ def decode_and_allgather(full, blocks_per_rank, block_size, decode_chunk, n_chun
         if world == 1:
             continue
         a, b = lo * block_size, hi * block_size
+        if peer is not None:
+            peer.push(rank * per + a, rank * per + b)
+            continue
         ops = []
         for d in range(1, world):                              # peer order staggered per rank: no hot receiver
             to, frm = (rank + d) % world, (rank - d) % world
@@ -83,6 +133,8 @@ def decode_and_allgather(full, blocks_per_rank, block_size, decode_chunk, n_chun
         works += dist.batch_isend_irecv(ops)
     for wk in works:
         wk.wait()
+    if peer is not None and world > 1:
+        peer.finish()
     return works
 
 

@@ -64,8 +64,10 @@ for row in csv.reader(io.StringIO(src)):
         tables.append(cur)
     elif cur is not None:
         cur["rows"].append(row)
-traffic = {"source": "ncu --set full, tag %s, %d blocks of 64 KB (datagen P50) per launch" % (tag, prof_blocks),
-           "proba": 0.5, "block_bytes": 65536}
+tpath = os.path.join(ROOT, "profiles", "traffic.json")
+traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+traffic.update({"proba": 0.5, "block_bytes": 65536})
+traffic.setdefault("sources", {})
 seen = set()
 for idx, v in enumerate(rr[2:]):
     m = dict(zip(h, v))
@@ -83,10 +85,13 @@ for idx, v in enumerate(rr[2:]):
     per_block = (rd + wr) / prof_blocks
     lines.append("  dram bytes per 64 KB block: %.0f   (algorithmic C+U for P50 = %.0f)" % (per_block, 6945762471 / 65536))
     lines.append("  warp-instructions per 64 KB block: %.0f" % (num(m["smsp__inst_executed.sum"]) / prof_blocks))
-    if "expand" in short:
-        traffic["expand_dram_bytes_per_block"] = round(per_block, 1)
-    elif "scan" in short:
-        traffic["scan_dram_bytes_per_block"] = round(per_block, 1)
+    src_note = "ncu --set full, tag %s, %d blocks of 64 KB (datagen P50) per launch" % (tag, prof_blocks)
+    if "expand_rows" in short:
+        traffic["expand_dram_bytes_per_block"] = round(per_block, 1); traffic["sources"]["expand"] = src_note
+    elif short.endswith("lz4_scan_kernel"):
+        traffic["scan_dram_bytes_per_block"] = round(per_block, 1); traffic["sources"]["scan"] = src_note
+    elif "encode_par" in short:
+        traffic["encode_par_dram_bytes_per_block"] = round(per_block, 1); traffic["sources"]["encode_par"] = src_note
     lines.append("  stalls per issued instruction (smsp__average_warps_issue_stalled_*_per_issue_active):")
     for k in sorted(h):
         if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio") and num(m[k]) >= 0.2:
@@ -105,6 +110,6 @@ for idx, v in enumerate(rr[2:]):
         mn = sorted(set(d[2].split()[0] if not d[2].startswith("@") else d[2].split()[1] for d in tma))
         lines.append("  TMA / mbarrier / cp.async instructions in the SASS: " + (", ".join(mn) if mn else "-"))
     lines.append("")
-json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+json.dump(traffic, open(tpath, "w"), indent=1)
 open(os.path.join(ROOT, "profiles", "ncu_%s_summary.txt" % tag), "w").write("\n".join(lines) + "\n")
 print("\n".join(lines[:70]))
