@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--chunks", type=int, default=4, help="N > 1: pieces of a rank's shard whose exchange overlaps the decode of the next piece")
+    ap.add_argument("--ceiling", action="store_true",
+                    help="also time the rows kernel's skeleton without the decode (TMA in/out only; + one LDS/STS per output byte)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = copy-engine pushes into the peers' frames (CUDA IPC over NVLink), 'nccl' = grouped NCCL send/recv")
     return ap.parse_args()
@@ -420,6 +422,30 @@ def run_ours(args):
     else:
         codec_ms_max = codec_ms
 
+    # ---- ceiling of the rows kernel's structure: the same persistent TMA-in -> smem -> TMA-out skeleton, no decode ----
+    ceiling = None
+    if args.ceiling and BLOCK == 65536:
+        import ctypes as C
+        fn = lib.LZ4B200_debug_ceiling
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+        st = torch.cuda.current_stream().cuda_stream
+        ceiling = {"what": "lz4_ceiling_kernel: one CTA per SM, TMA bulk load of each compressed block, TMA bulk store of 64 KB, "
+                           "same batch; the bytes written are meaningless"}
+        for mode, key in ((0, "tma_only"), (1, "tma_plus_one_lds_sts_per_byte")):
+            for _ in range(2):
+                assert fn(packed.data_ptr(), offs.data_ptr(), csizes.data_ptr(), out.data_ptr(), BLOCK, n_blocks, mode, st) == 0
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                fn(packed.data_ptr(), offs.data_ptr(), csizes.data_ptr(), out.data_ptr(), BLOCK, n_blocks, mode, st)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / K
+            ceiling[key] = {"ms": round(ms, 4), "GBps_algorithmic": round((comp_bytes + total) / (ms * 1e-3) / GB, 1)}
+        decode()                                             # restore the decoded bytes
+        torch.cuda.synchronize()
+
     # ---- e2e: same workload through the host-buffer C-ABI call, pinned host memory ----
     e2e = None
     if not args.no_e2e:
@@ -525,7 +551,7 @@ def run_ours(args):
                               "ms": round(codec_ms, 4), "achieved": round(step_achieved, 2),
                               "frac": round(step_achieved / peak, 4), "traffic": step_traffic},
                      "traffic_source": traffic_src,
-                     "peak_source": peak_source},
+                     "peak_source": peak_source, **({"ceiling": ceiling} if ceiling else {})},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "compress": {"GBps": round(total / (compress_ms * 1e-3) / GB, 3), "ms": round(compress_ms, 3),

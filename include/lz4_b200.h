@@ -178,6 +178,15 @@ LZ4B200_API int LZ4B200_pack_frame_blocks(const void* d_slots, int64_t slotStrid
                                           const void* d_src, int64_t srcStride, int32_t blockSize, int32_t lastSize,
                                           int64_t nBlocks, void* d_body, int64_t* d_outOff, void* stream);
 
+/*
+ * Multi-GPU reassembly (the ordered-writer role of programs/lz4io.c:594-635 when every GPU decodes a shard of a frame):
+ * enqueue on `stream` the copy of `bytes` device bytes from d_src (current device) to d_dstPeer, memory of device
+ * `peerDevice` that is mapped into this process (cudaIpcOpenMemHandle / a same-process allocation).  Peer access is
+ * enabled on first use; the copy runs on a copy engine over NVLink and takes no SM from the codec kernels.
+ * Returns LZ4B200_OK, LZ4B200_ERR_ARG (the devices cannot reach each other directly) or LZ4B200_ERR_CUDA.
+ */
+LZ4B200_API int LZ4B200_peer_copy_async(void* d_dstPeer, int peerDevice, const void* d_src, size_t bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * 3. Host-buffer batch calls (synchronous): the batch layer with the host<->device copies inside,
  *    pipelined over chunks.  h_* are host pointers (pinned memory gives full PCIe speed).

@@ -35,6 +35,7 @@ PROTOTYPES = [
     ("LZ4B200_compress_blocks_parallel", C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _i32, C.c_int, _vp, _i64, _vp]),
     ("LZ4B200_pack_blocks", C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, C.c_int, _vp]),
     ("LZ4B200_pack_frame_blocks", C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp, _vp]),
+    ("LZ4B200_peer_copy_async", C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _vp]),
     ("LZ4B200_decompress_blocks_host", C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64]),
     ("LZ4B200_compress_blocks_host", C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _i32, C.c_int, _vp, _i64]),
     ("LZ4B200_compressFrameBound", _i64, [_i64, C.c_int]),

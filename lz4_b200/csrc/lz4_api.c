@@ -44,6 +44,40 @@ const char* LZ4B200_last_cuda_error(void) { return g_cuda_error; }
 uint64_t LZ4B200_launch_count(void) { return lz4k_launch_count(); }
 /* not part of the public header: developer hook used by tests/perf/phase_timing.py */
 __attribute__((visibility("default"))) int LZ4B200_debug_phase_cycles(unsigned long long* out8) { return lz4k_debug_phase_cycles(out8); }
+int LZ4B200_peer_copy_async(void* d_dstPeer, int peerDevice, const void* d_src, size_t bytes, void* stream)
+{
+    static unsigned char enabled[64][64];
+    int cur = 0;
+    cudaError_t e;
+    if (bytes == 0) return LZ4B200_OK;
+    if (!d_dstPeer || !d_src || peerDevice < 0 || peerDevice >= 64) return LZ4B200_ERR_ARG;
+    e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (cur >= 64) return LZ4B200_ERR_ARG;
+    if (cur != peerDevice && !enabled[cur][peerDevice]) {
+        int can = 0;
+        e = cudaDeviceCanAccessPeer(&can, cur, peerDevice);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceCanAccessPeer");
+        if (!can) return LZ4B200_ERR_ARG;
+        e = cudaDeviceEnablePeerAccess(peerDevice, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+        enabled[cur][peerDevice] = 1;
+    }
+    e = cudaMemcpyAsync(d_dstPeer, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+    return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "cudaMemcpyAsync (peer)");
+}
+
+/* not part of the public header: developer hook used by bench.py --ceiling (the rows kernel's skeleton without the decode) */
+__attribute__((visibility("default"))) int LZ4B200_debug_ceiling(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
+                                                                  void* d_dst, int64_t dstStride, int64_t nBlocks, int mode, void* stream)
+{
+    lz4k_decode_args a;
+    memset(&a, 0, sizeof a);
+    a.src = (const uint8_t*)d_src; a.srcOff = d_srcOff; a.srcSize = d_srcSize;
+    a.dst = (uint8_t*)d_dst; a.dstStride = dstStride; a.nBlocks = nBlocks;
+    return lz4k_launch_ceiling(&a, mode, stream);
+}
 int LZ4B200_device_count(void)
 {
     int n = 0;

@@ -731,6 +731,60 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
     if (tid == 0) tma_wait_all0();
 }
 
+/* ---- ceiling of the rows kernel's skeleton (developer tool; bench.py --ceiling) ----
+ * Same persistent structure -- one CTA of 1024 threads per SM, TMA bulk load of the compressed block into `in`, TMA bulk
+ * store of 64 KB from `out` -- with the decode replaced by
+ *   mode 0: nothing (load b+1 and store b are both in flight): what HBM and the TMA path give this structure;
+ *   mode 1: one LDS.U8 + STS.U8 per output byte, one byte per thread, 4096-byte waves with a CTA barrier each: the floor
+ *           of moving every byte through shared memory at byte granularity, without any address resolution.
+ * The bytes written are meaningless; the timing is the point. */
+__global__ void __launch_bounds__(kRowsThreads, 1) lz4_ceiling_kernel(lz4k_decode_args a, int mode)
+{
+    extern __shared__ __align__(16) uint8_t smemRaw[];
+    RowsSmem& S = *reinterpret_cast<RowsSmem*>(smemRaw);
+    const int tid = threadIdx.x;
+    const uint32_t sBase = smem_u32(smemRaw);
+    const uint32_t outS = sBase + (uint32_t)offsetof(RowsSmem, out), inS = sBase + (uint32_t)offsetof(RowsSmem, in);
+    uint32_t parity = 0;
+    auto issueLoad = [&](int64_t b) {
+        const uint8_t* src = a.src + a.srcOff[b];
+        const int n = a.srcSize[b];
+        const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+        const uint32_t loadBytes = (uint32_t)((head + n + 15) & ~15);
+        mbar_expect_tx(&S.mbar, loadBytes);
+        for (uint32_t o = 0; o < loadBytes; o += 16384u) tma_load_1d(S.in + o, src - head + o, min(16384u, loadBytes - o), &S.mbar);
+    };
+    if (tid == 0) { mbar_init(&S.mbar, 1); }
+    __syncthreads();
+    if (tid == 0 && blockIdx.x < a.nBlocks) issueLoad(blockIdx.x);
+    for (int64_t b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
+        mbar_wait(&S.mbar, parity);
+        parity ^= 1;
+        if (mode >= 1) {
+            if (tid == 0) tma_wait_read0();                    /* the previous store has finished reading `out` */
+            __syncthreads();
+            for (int wv = 0; wv < 65536 / kWave; wv++) {
+                uint32_t v[kRowsRpt];
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++) v[r] = lds_u8(inS + (uint32_t)((wv * kWave + r * kRowsThreads + tid) & 0x7FFF));
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++) sts_u8(outS + (uint32_t)(wv * kWave + r * kRowsThreads + tid), v[r]);
+                __syncthreads();
+            }
+            fence_proxy_async();
+            __syncthreads();
+        }
+        if (tid == 0) {
+            if (b + gridDim.x < a.nBlocks) issueLoad(b + gridDim.x);
+            uint8_t* dst = a.dst + b * a.dstStride;
+            for (uint32_t o = 0; o < 65536u; o += 16384u) tma_store_1d(dst + o, S.out + o, 16384u);
+            tma_commit();
+        }
+        if (mode >= 1) __syncthreads();
+    }
+    if (tid == 0) tma_wait_all0();
+}
+
 /* =============================================================================================
  * encode: one warp per block, byte-identical replay of LZ4_compress_generic_validated
  * ============================================================================================= */
@@ -1148,6 +1202,20 @@ int lz4k_launch_encode(const lz4k_encode_args* a, void* stream)
     if (grid > a->nBlocks) grid = a->nBlocks;
     lz4_encode_kernel<<<(unsigned)grid, 32, kEncodeTableBytes, s>>>(*a);
     g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int lz4k_launch_ceiling(const lz4k_decode_args* a, int mode, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->nBlocks == 0) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(lz4_ceiling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
+    if (e != cudaSuccess) return (int)e;
+    const int64_t grid = a->nBlocks < sms ? a->nBlocks : sms;
+    lz4_ceiling_kernel<<<(unsigned)grid, kRowsThreads, sizeof(RowsSmem), s>>>(*a, mode);
     return (int)cudaGetLastError();
 }
 

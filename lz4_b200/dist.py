@@ -57,13 +57,15 @@ class PeerFrame:
     """Every rank's copy of the frame, mapped into every other rank's address space (CUDA IPC; NVLink peer memory).
 
     With it the exchange of a decoded chunk is R-1 device-to-device copies issued by the rank that decoded it, straight
-    into the chunk's final place in each peer's frame.  The copies run on the GPU's copy engines, one stream per peer:
+    into the chunk's final place in each peer's frame (LZ4B200_peer_copy_async).  The copies run on the GPU's copy engines, one stream per peer:
     they take no SM away from the codec's persistent kernels -- NCCL's send/recv kernels do, which made the overlapped
     NCCL exchange SLOWER than the serial one (2 GPUs, 4 GiB per rank: 19.5 ms with 4 chunks, 16.5 ms with one;
     profiles/experiments_r02.txt).  Collective construction: every rank of `group` must call it with its own `full`."""
 
     def __init__(self, full, group=None):
         from torch.multiprocessing.reductions import reduce_tensor
+        from . import _lib
+        self.lib = _lib.load()
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -87,8 +89,10 @@ class PeerFrame:
             r = (self.rank + 1 + i) % self.world               # staggered: no hot receiver
             st = self.streams[i]
             st.wait_event(ev)
-            with torch.cuda.stream(st):
-                self.peers[r][lo:hi].copy_(self.full[lo:hi], non_blocking=True)
+            rc = self.lib.LZ4B200_peer_copy_async(self.peers[r].data_ptr() + lo, self.peers[r].device.index,
+                                                  self.full.data_ptr() + lo, hi - lo, st.cuda_stream)
+            if rc != 0:
+                raise RuntimeError("LZ4B200_peer_copy_async failed (%d): %s" % (rc, self.lib.LZ4B200_last_cuda_error().decode()))
 
     def finish(self):
         """Order the current stream after this rank's pushes and after every peer's pushes into this rank."""

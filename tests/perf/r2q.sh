@@ -20,6 +20,5 @@ PY
 }
 run peer_c4 --exchange peer --chunks 4
 run peer_c8 --exchange peer --chunks 8
-run peer_c16 --exchange peer --chunks 16
+run peer_c2 --exchange peer --chunks 2
 run peer_c1 --exchange peer --chunks 1
-run nccl_c1 --exchange nccl --chunks 1
