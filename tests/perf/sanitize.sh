@@ -6,10 +6,10 @@ cd "$(dirname "$0")/../.."
 TAG=${1:-r02}
 O=gpurun_out/sanitizer_$TAG.txt
 mkdir -p gpurun_out
-T="tests/test_gpu_parity.py::test_decode_noisy_source_vs_oracle tests/test_gpu_parity.py::test_mixed_batch_fast_and_slow_lists tests/test_gpu_parity.py::test_compress_random_vs_oracle tests/test_gpu_parity.py::test_decode_overlap_and_long_runs"
+T="tests/test_gpu_parity.py::test_decode_noisy_source_vs_oracle tests/test_gpu_parity.py::test_mixed_batch_fast_and_slow_lists tests/test_gpu_parity.py::test_compress_random_vs_oracle tests/test_gpu_parity.py::test_decode_overlap_and_long_runs tests/test_gpu_parallel_compress.py::test_special_shapes_long_runs_and_long_literals tests/test_gpu_parallel_compress.py::test_limited_output_and_never_past_capacity tests/test_frame.py::test_gpu_frames_byte_identical_and_roundtrip"
 : > $O
 run() {   # run <title> <tool> [env...]
-  echo "===== $1: compute-sanitizer --tool $2  (python -m pytest <4 parity tests> -m gpu)" >> $O
+  echo "===== $1: compute-sanitizer --tool $2  (python -m pytest <7 parity tests> -m gpu)" >> $O
   shift; tool=$1; shift
   env "$@" timeout 1500 compute-sanitizer --tool $tool --print-limit 12 python -m pytest $T -x -q -m gpu 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|Error|hazard" | cut -c1-200 | tail -16 >> $O
 }
