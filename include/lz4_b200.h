@@ -95,9 +95,12 @@ LZ4B200_API uint64_t LZ4B200_launch_count(void);
 /* Bytes of device workspace LZ4B200_decompress_blocks needs for nBlocks blocks of ANY capacity
  * (worst case: 32 KB of sequence marks per block). */
 LZ4B200_API size_t LZ4B200_decompress_workspace_bytes(int64_t nBlocks);
-/* The exact requirement of one call: perBlockCaps != 0 when d_dstCap is passed, else the uniform dstCap.
- * Marks are sized by the capacity (dstCap/4 + 2 slots, at most 8192; none for blocks above 64 KB), so
- * batches of small blocks need little workspace.  Always <= LZ4B200_decompress_workspace_bytes(nBlocks). */
+/* The workspace one call wants: perBlockCaps != 0 when d_dstCap is passed, else the uniform dstCap.
+ * Marks are sized by the capacity (dstCap/4 + 2 slots, at most 8192), so batches of small blocks need little
+ * workspace (<= LZ4B200_decompress_workspace_bytes(nBlocks)).  A batch of blocks ABOVE 64 KB with a uniform capacity
+ * of at most 64 MB (lz4frame's 256 KB .. 4 MB blocks) is decoded in 60 KB output tiles and wants two words per possible
+ * sequence, i.e. about 2 x dstCap bytes per block; with a smaller workspace (at least
+ * LZ4B200_decompress_workspace_bytes(nBlocks)) such a batch is still decoded, by the slow one-warp-per-block kernel. */
 LZ4B200_API size_t LZ4B200_decompress_workspace_bytes_for(int64_t nBlocks, int perBlockCaps, int32_t dstCap);
 
 /*

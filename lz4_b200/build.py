@@ -18,6 +18,7 @@ NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 SOURCES = ["lz4_kernels.cu", "lz4_api.c"]
 HEADERS = [os.path.join(CSRC, "lz4_kernels.h"), os.path.join(CSRC, "lz4_rows_core.h"),
            os.path.join(CSRC, "lz4_scan_core.h"), os.path.join(CSRC, "lz4_scan_par.h"),
+           os.path.join(CSRC, "lz4_scan_split.h"), os.path.join(CSRC, "lz4_encode_par.cuh"),
            os.path.join(ROOT, "include", "lz4_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -173,7 +173,7 @@ int LZ4B200_decompress_blocks_phased(const void* d_src, const int64_t* d_srcOff,
     if (nBlocks < 0) return LZ4B200_ERR_ARG;
     if (nBlocks == 0) return LZ4B200_OK;
     if (!d_src || !d_srcOff || !d_srcSize || !d_dst || !d_outSize || !d_workspace) return LZ4B200_ERR_ARG;
-    if (workspaceBytes < lz4k_decode_workspace_bytes_for(nBlocks, d_dstCap != NULL, dstCap)) return LZ4B200_ERR_ARG;
+    if (workspaceBytes < lz4k_decode_workspace_bytes_min(nBlocks, d_dstCap != NULL, dstCap)) return LZ4B200_ERR_ARG;
     a.src = (const uint8_t*)d_src; a.srcOff = d_srcOff; a.srcSize = d_srcSize;
     a.dst = (uint8_t*)d_dst; a.dstOff = d_dstOff; a.dstStride = dstStride;
     a.dstCapArr = d_dstCap; a.dstCap = dstCap; a.outSize = d_outSize; a.nBlocks = nBlocks;

@@ -118,18 +118,24 @@ struct WsHeader { uint32_t slowCount, pad[3]; };
 
 struct WsView {
     WsHeader* hdr; uint32_t* nSeq; uint32_t* slowList; uint32_t* marks; uint32_t* scratch; uint32_t markStride;
+    uint32_t* tileFirst; uint32_t* tileFlag; uint32_t tilesMax;    /* batches of blocks above 64 KB (wide marks): see lz4_expand_tiles_kernel */
 };
+constexpr int kTile = 61440;                       /* output bytes per tile of a block above 64 KB: 15 waves of 4096 */
+constexpr int32_t kTileMaxCap = 64 << 20;          /* larger capacities take the generic kernel (the marks would need 2 x capacity) */
+__host__ __device__ inline bool wide_batch(const int32_t* dstCapArr, int32_t dstCap) { return !dstCapArr && dstCap > 65536 && dstCap <= kTileMaxCap; }
+__host__ __device__ inline uint32_t tiles_of(int32_t bytes) { return ((uint32_t)bytes + (uint32_t)kTile - 1u) / (uint32_t)kTile; }
 /* mark slots per block: a block the shared-memory expand kernel may take (capacity <= 64 KB) has at most
  * capacity/4 + 1 sequences (every sequence but the last produces >= 4 bytes) and the scan visits at most one more;
  * batches of larger blocks need no marks at all */
-__host__ __device__ inline uint32_t mark_stride(const int32_t* dstCapArr, int32_t dstCap)
+__host__ __device__ inline uint32_t mark_stride(const int32_t* dstCapArr, int32_t dstCap, bool wide = false)
 {
     if (dstCapArr) return (uint32_t)kMaxSeqFast;               /* per-block capacities live on the device: worst case */
+    if (wide) return 2u * ((uint32_t)dstCap / 4u + 2u);        /* wide marks: two words per sequence */
     if (dstCap <= 0 || dstCap > 65536) return 0u;
     const uint32_t s = (uint32_t)dstCap / 4u + 2u;
     return s < (uint32_t)kMaxSeqFast ? s : (uint32_t)kMaxSeqFast;
 }
-__host__ __device__ inline WsView ws_view(void* ws, int64_t n, uint32_t markStride)
+__host__ __device__ inline WsView ws_view(void* ws, int64_t n, uint32_t markStride, uint32_t tilesMax = 0)
 {
     WsView v;
     uint8_t* p = reinterpret_cast<uint8_t*>(ws);
@@ -139,9 +145,33 @@ __host__ __device__ inline WsView ws_view(void* ws, int64_t n, uint32_t markStri
     v.marks = reinterpret_cast<uint32_t*>(p); p += (((size_t)n * markStride * 4 + 255) / 256) * 256;
     v.scratch = reinterpret_cast<uint32_t*>(p);                /* split scan: 2 x markStride words per block */
     v.markStride = markStride;
+    /* wide batches have no scratch lists: per block tilesMax + 1 first-sequence indices, tilesMax done flags + 1 "gave up" word */
+    v.tileFirst = reinterpret_cast<uint32_t*>(p); p += (((size_t)n * (tilesMax + 1) * 4 + 255) / 256) * 256;
+    v.tileFlag = reinterpret_cast<uint32_t*>(p);
+    v.tilesMax = tilesMax;
     return v;
 }
-__device__ __forceinline__ WsView ws_view(const lz4k_decode_args& a) { return ws_view(a.workspace, a.nBlocks, mark_stride(a.dstCapArr, a.dstCap)); }
+__host__ __device__ inline size_t ws_bytes(int64_t nBlocks, uint32_t markStride, uint32_t tilesMax = 0)
+{
+    const size_t lst = (((size_t)nBlocks * 4 + 255) / 256) * 256;
+    const size_t mk = (((size_t)nBlocks * markStride * sizeof(uint32_t) + 255) / 256) * 256;
+    if (tilesMax) {                                            /* header | nSeq | slowList | wide marks | tileFirst | tileFlag */
+        const size_t tl = (((size_t)nBlocks * (tilesMax + 1) * 4 + 255) / 256) * 256;
+        return 256 + 2 * lst + mk + 2 * tl + 256;
+    }
+    return 256 + 2 * lst + 3 * mk + 256;                      /* header | nSeq | slowList | marks | scratch (2 x marks) */
+}
+/* A batch of blocks above 64 KB is decoded in tiles when the caller's workspace has room for the wide marks
+ * (LZ4B200_decompress_workspace_bytes_for says how much); with the small workspace it takes the generic kernel. */
+__host__ __device__ inline bool use_wide(const int32_t* dstCapArr, int32_t dstCap, int64_t nBlocks, size_t workspaceBytes)
+{
+    return wide_batch(dstCapArr, dstCap) && workspaceBytes >= ws_bytes(nBlocks, mark_stride(dstCapArr, dstCap, true), tiles_of(dstCap));
+}
+__device__ __forceinline__ WsView ws_view(const lz4k_decode_args& a)
+{
+    const bool wide = use_wide(a.dstCapArr, a.dstCap, a.nBlocks, a.workspaceBytes);
+    return ws_view(a.workspace, a.nBlocks, mark_stride(a.dstCapArr, a.dstCap, wide), wide ? tiles_of(a.dstCap) : 0u);
+}
 
 /* a block the shared-memory expand kernel takes: input and output fit its 64 KB windows, marks for every sequence */
 __device__ __forceinline__ bool rows_eligible(int n, int cap, uint32_t nseq, uint32_t markStride)
@@ -304,11 +334,28 @@ __global__ void __launch_bounds__(kScanLanes) lz4_scan_par_kernel(lz4k_decode_ar
         const uint8_t* src = a.src + a.srcOff[b];
         const int n = a.srcSize[b];
         const int cap = a.dstCapArr ? a.dstCapArr[b] : a.dstCap;
-        const bool wantMarks = (n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && w.markStride > 0);
-        uint32_t* marks = wantMarks ? (w.marks + b * w.markStride) : nullptr;
+        const bool wide = w.tilesMax != 0;                            /* a batch of blocks above 64 KB: two-word marks for the tiles kernel */
+        const bool wantMarks = wide ? n > 0 : (n > 0 && n <= 65535 && cap > 0 && cap <= 65536 && w.markStride > 0);
+        uint32_t* marks = wantMarks ? (w.marks + (size_t)b * w.markStride) : nullptr;
+        const uint32_t markCap = wide ? w.markStride / 2u : w.markStride;
         int r = -1;
         uint32_t ns = 0;
-        if (n > 0 && n <= 65535 && cap > 0) {
+        if (wide && n > 0 && n <= 65535) {
+            const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+            const uint32_t loadBytes = (uint32_t)((head + n + 15) & ~15);
+            if (tid == 0) {
+                mbar_expect_tx(&S.mbar, loadBytes);
+                for (uint32_t o = 0; o < loadBytes; o += 16384u)
+                    tma_load_1d(S.in + o, src - head + o, min(16384u, loadBytes - o), &S.mbar);
+            }
+            while (!mbar_try_wait(&S.mbar, parity)) { }
+            parity ^= 1;
+            MemPtr<false, true> mem{S.in + head};
+            scan_par_block(S, mem, n, cap, marks, markCap, r, ns);
+        } else if (wide && n > 65535) {
+            MemPtr<true, true> mem{src};
+            scan_par_block(S, mem, n, cap, marks, markCap, r, ns);
+        } else if (n > 0 && n <= 65535 && cap > 0) {
             const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
             const uint32_t loadBytes = (uint32_t)((head + n + 15) & ~15);
             if (tid == 0) {
@@ -332,7 +379,34 @@ __global__ void __launch_bounds__(kScanLanes) lz4_scan_par_kernel(lz4k_decode_ar
         if (tid == 0) {
             a.outSize[b] = r;
             w.nSeq[b] = ns;
-            if (r > 0 && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
+            const bool tiled = wide && ns <= markCap;                 /* lz4_expand_tiles_kernel takes it */
+            if (r > 0 && !tiled && !rows_eligible(n, cap, ns, w.markStride)) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
+        }
+    }
+}
+
+/* ---- wide batches: per tile of kTile output bytes the first sequence whose match starts in or beyond it ----
+ * tileFirst[b][t] = min { k : matchStart(k) >= t * kTile } for t = 0 .. tiles(b) (nseq if none); done flags cleared.
+ * The match starts are non-decreasing in k and the last mark holds the decoded size, so sequence k's neighbours decide. */
+__global__ void __launch_bounds__(256) lz4_tile_index_kernel(lz4k_decode_args a)
+{
+    const WsView w = ws_view(a);
+    for (int64_t b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
+        uint32_t* first = w.tileFirst + (size_t)b * (w.tilesMax + 1);
+        uint32_t* flag = w.tileFlag + (size_t)b * (w.tilesMax + 1);
+        for (uint32_t t = threadIdx.x; t <= w.tilesMax; t += blockDim.x) flag[t] = 0u;
+        const int total = a.outSize[b];
+        const uint32_t ns = w.nSeq[b];
+        if (total <= 0 || ns == 0 || ns > w.markStride / 2u) continue;
+        const uint32_t nT = tiles_of(total);
+        const uint32_t* marks = w.marks + (size_t)b * w.markStride;
+        for (uint32_t k = threadIdx.x; k < ns; k += blockDim.x) {
+            const uint32_t m = marks[2 * (size_t)k + 1];
+            const uint32_t t1 = min(m / (uint32_t)kTile, nT);             /* tiles t <= t1 start at or below m */
+            uint32_t t0 = 0;                                                /* first tile not yet served by k - 1 */
+            if (k) t0 = min(marks[2 * (size_t)k - 1] / (uint32_t)kTile, nT) + 1u;
+            for (uint32_t t = t0; t <= t1; t++) first[t] = k;
+            if (k + 1 == ns) for (uint32_t t = t1 + 1; t <= nT; t++) first[t] = ns;
         }
     }
 }
@@ -731,6 +805,224 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_rows_kernel(lz4k_d
     if (tid == 0) tma_wait_all0();
 }
 
+/* =============================================================================================
+ * expand (tiles): blocks ABOVE 64 KB (lz4frame's 256 KB .. 4 MB blocks), one CTA per 60 KB OUTPUT TILE
+ *
+ * The rows formulation applied to a window of a big block.  The scan (lz4_scan_par_kernel) leaves wide marks
+ * {token position, match start} per sequence and lz4_tile_index_kernel the first sequence of every tile; a unit of work is
+ * (block b, tile t) = output bytes [t * kTile, (t + 1) * kTile) of block b.  Differences to lz4_expand_rows_kernel:
+ *   - the sequences that overlap the tile are parsed from GLOBAL memory (their tokens may lie megabytes apart from the
+ *     tile's literals) and their runs are clipped to the tile (rw_tile_runs);
+ *   - the compressed block is not staged: a literal run's delta maps into a virtual range [kLitBase, ...) that means
+ *     "byte x - kLitBase of the compressed block", read from global memory through the read-only cache;
+ *   - a match source below the tile start lies in an EARLIER tile of the same block: it is read from the destination
+ *     in global memory (L2).  Tile t therefore waits, after its passes 1-2 and before its waves, for tile t - 1's flag,
+ *     which that tile's CTA sets once its bulk store has completed.  Units are numbered tile-major (all blocks' tile 0,
+ *     then tile 1, ...) and taken in ascending order by a grid of resident CTAs, so a tile's predecessor was started
+ *     earlier: no deadlock; with >= 148 blocks in the batch the wait is over before it begins.
+ *   - a tile with more runs than the table holds hands its block to the generic kernel (which rewrites the whole block).
+ * ============================================================================================= */
+constexpr uint32_t kLitBase = 1u << 28;                   /* virtual window addresses >= kLitBase: compressed byte (address - kLitBase) */
+constexpr uint32_t kZeroV = kLitBase + (1u << 27);         /* the always-zero cell (offset 0, lz4.c:2407) */
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool FULL>
+__device__ __forceinline__ void tiles_resolve(uint32_t (&sa)[LZ4K_ROWS_RPT], const uint32_t p0, const uint32_t waveS,
+                                              const uint32_t lim, const uint32_t outS, const uint32_t rowsS,
+                                              const uint32_t tabS, const uint32_t le)
+{
+    const uint32_t rowAddr = rowsS + ((p0 >> 5) << 3);
+    bool any = false;
+    #pragma unroll
+    for (int r = 0; r < LZ4K_ROWS_RPT; r++) {
+        sa[r] = outS + 65536u;                                  /* (a byte past the tile: never read, never "inside the wave") */
+        if (FULL || p0 + (uint32_t)(r * 1024) < lim) {
+            const uint2 row = lds_u64(rowAddr + (uint32_t)(r * 32 * 8));
+            const uint32_t j = row.y + (uint32_t)__popc(row.x & le);
+            sa[r] = outS + p0 + (uint32_t)(r * 1024) + lds_u32(tabS + (j << 2));
+        }
+        any |= (sa[r] - waveS) < (uint32_t)kWave;
+    }
+    while (any) {                                               /* sources inside this wave: follow them */
+        any = false;
+        #pragma unroll
+        for (int r = 0; r < LZ4K_ROWS_RPT; r++) {
+            uint32_t x = sa[r];
+            if ((x - waveS) < (uint32_t)kWave) {
+                const uint32_t q = x - outS;
+                const uint2 row = lds_u64(rowsS + ((q >> 5) << 3));
+                const uint32_t j = row.y + (uint32_t)__popc(row.x & (0xFFFFFFFFu >> (31u - (q & 31u))));
+                x += lds_u32(tabS + (j << 2));
+                sa[r] = x;
+            }
+            any |= (x - waveS) < (uint32_t)kWave;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_tiles_kernel(lz4k_decode_args a)
+{
+    extern __shared__ __align__(16) uint8_t smemRaw[];
+    RowsSmem& S = *reinterpret_cast<RowsSmem*>(smemRaw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const WsView w = ws_view(a);
+    const uint32_t le = lanemask_le();
+    const uint32_t sBase = smem_u32(smemRaw);
+    const uint32_t outS = sBase + (uint32_t)offsetof(RowsSmem, out);
+    const uint32_t rowsS = sBase + (uint32_t)offsetof(RowsSmem, rows), tabS = sBase + (uint32_t)offsetof(RowsSmem, tab);
+    const uint32_t tilesMax = w.tilesMax;
+    uint32_t wpar = 0;
+    uint32_t* pendFlag = nullptr;                               /* thread 0: flag of the unit whose bulk store is in flight */
+    auto publishPending = [&]() {                               /* thread 0 */
+        tma_wait_all0();                                        /* the store has completed (not only finished reading `out`) */
+        if (pendFlag) { __threadfence(); st_release_gpu(pendFlag, 1u); pendFlag = nullptr; }
+    };
+    if (tid == 0) mbar_init(&S.wbar, kRowsThreads / 32);
+    __syncthreads();
+
+    const int64_t units = a.nBlocks * (int64_t)tilesMax;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int64_t b = u % a.nBlocks;
+        const uint32_t t = (uint32_t)(u / a.nBlocks);
+        const int total = a.outSize[b];
+        const uint32_t nseq = w.nSeq[b];
+        uint32_t* flags = w.tileFlag + (size_t)b * (tilesMax + 1);
+        if (!(total > 0 && nseq > 0 && nseq <= w.markStride / 2u && t < tiles_of(total))) {     /* (the same for every thread) */
+            if (tid == 0 && pendFlag) publishPending();
+            continue;
+        }
+        const uint8_t* src = a.src + a.srcOff[b];
+        uint8_t* dstB = a.dst + (a.dstOff ? a.dstOff[b] : b * a.dstStride);
+        const uint32_t* marks = w.marks + (size_t)b * w.markStride;
+        const uint32_t* first = w.tileFirst + (size_t)b * (tilesMax + 1);
+        const int os = (int)(t * (uint32_t)kTile), oe = min(os + kTile, total), len = oe - os;
+        const uint32_t f0 = first[t], f1 = first[t + 1];
+        const int k0 = f0 ? (int)f0 - 1 : 0, k1 = (int)min(f1 + 1u, nseq);
+        const uint32_t litBase = kLitBase - outS + (uint32_t)os;
+        const int zeroDelta0 = (int)(kZeroV - outS + (uint32_t)os);
+        auto parse = [&](int k) { return rw_parse_wide(src, marks[2 * (size_t)k], marks[2 * (size_t)k + 1], k + 1 == (int)nseq); };
+
+        for (int k = tid; k < 2048; k += kRowsThreads) S.rows[k] = make_uint2(0u, 0u);
+        __syncthreads();
+        /* ---- runs, pass 1 ---- */
+        for (int k = k0 + tid; k < k1; k += kRowsThreads) {
+            const RwSeq s = parse(k);
+            rw_tile_runs(s, os, oe, litBase, zeroDelta0, [&](int st, int) { atomicOr(&S.rows[st >> 5].x, 1u << (st & 31)); });
+        }
+        __syncthreads();
+        /* ---- rank ---- */
+        {
+            constexpr int WPT = 2048 / kRowsThreads;
+            uint32_t cnt[WPT], x = 0;
+            #pragma unroll
+            for (int j = 0; j < WPT; j++) { cnt[j] = __popc(S.rows[tid * WPT + j].x); x += cnt[j]; }
+            uint32_t incl = x;
+            #pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { uint32_t y = __shfl_up_sync(kFull, incl, dd); if (lane >= dd) incl += y; }
+            if (lane == 31) S.warpSum[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t v = S.warpSum[lane];
+                #pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) { uint32_t y = __shfl_up_sync(kFull, v, dd); if (lane >= dd) v += y; }
+                S.warpSum[lane] = v;
+                if (lane == 31) S.nRuns = v;
+            }
+            __syncthreads();
+            uint32_t ex = incl - x + (warp ? S.warpSum[warp - 1] : 0);
+            #pragma unroll
+            for (int j = 0; j < WPT; j++) { S.rows[tid * WPT + j].y = ex - 1u; ex += cnt[j]; }
+        }
+        const uint32_t nRuns = S.nRuns;
+        if (tid == 0) publishPending();                        /* the previous unit's store is complete: its flag goes up, `out` is free */
+        __syncthreads();
+        if (nRuns > (uint32_t)kRowsMaxRuns) {                  /* (pathological) the generic kernel redoes the whole block */
+            if (tid == 0) {
+                if (atomicExch(&flags[tilesMax], 1u) == 0u) w.slowList[atomicAdd(&w.hdr->slowCount, 1u)] = (uint32_t)b;
+                __threadfence();
+                st_release_gpu(&flags[t], 1u);                 /* whoever waits for this tile may go on: its bytes will be rewritten */
+            }
+            __syncthreads();
+            continue;
+        }
+        /* ---- runs, pass 2 ---- */
+        for (int k = k0 + tid; k < k1; k += kRowsThreads) {
+            const RwSeq s = parse(k);
+            rw_tile_runs(s, os, oe, litBase, zeroDelta0, [&](int st, int d) { S.tab[rw_rank(S.rows, (uint32_t)st)] = (uint32_t)d; });
+        }
+        __syncthreads();
+        /* ---- the tile before this one must be in global memory ---- */
+        if (t > 0) {
+            if (tid == 0) { while (ld_acquire_gpu(&flags[t - 1]) == 0u) __nanosleep(200); }
+            __syncthreads();
+        }
+        /* ---- waves ---- */
+        {
+            const int nWaves = (len + kWave - 1) / kWave;
+            uint32_t sa[kRowsRpt];
+            auto resolve = [&](int wv) {
+                const uint32_t p0 = (uint32_t)(wv * kWave + tid);
+                if ((wv + 1) * kWave <= len) tiles_resolve<true>(sa, p0, outS + (uint32_t)(wv * kWave), 0xFFFFFFFFu, outS, rowsS, tabS, le);
+                else tiles_resolve<false>(sa, p0, outS + (uint32_t)(wv * kWave), (uint32_t)len, outS, rowsS, tabS, le);
+            };
+            resolve(0);
+            for (int wv = 0; wv < nWaves; wv++) {
+                if (wv > 0) { mbar_wait(&S.wbar, wpar); wpar ^= 1; }   /* every warp has copied wave wv-1 */
+                const uint32_t p0 = (uint32_t)(wv * kWave + tid);
+                const uint32_t lim = ((wv + 1) * kWave <= len) ? 0xFFFFFFFFu : (uint32_t)len;
+                uint32_t v[kRowsRpt];
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++) {
+                    const uint32_t x = sa[r];
+                    v[r] = 0u;
+                    if (p0 + (uint32_t)(r * kRowsThreads) < lim) {
+                        if (x >= kLitBase) v[r] = (x == kZeroV) ? 0u : (uint32_t)__ldg(src + (x - kLitBase));
+                        else if (x >= outS) v[r] = lds_u8(x);
+                        else v[r] = (uint32_t)__ldcg(dstB + (os - (int)(outS - x)));
+                    }
+                }
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++)
+                    if (p0 + (uint32_t)(r * kRowsThreads) < lim) sts_u8(outS + p0 + (uint32_t)(r * kRowsThreads), v[r]);
+                if (wv == nWaves - 1) fence_proxy_async();     /* generic-proxy writes of `out` before the bulk store reads them */
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.wbar);
+                if (wv + 1 < nWaves) resolve(wv + 1);
+            }
+            mbar_wait(&S.wbar, wpar);
+            wpar ^= 1;
+        }
+        /* ---- store: smem -> HBM ---- */
+        {
+            uint8_t* dst = dstB + os;
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                const uint32_t bulk = (uint32_t)len & ~15u;
+                if (tid == 0 && bulk) {
+                    for (uint32_t o = 0; o < bulk; o += 16384u) tma_store_1d(dst + o, S.out + o, min(16384u, bulk - o));
+                    tma_commit();
+                }
+                if (tid < (len & 15)) { dst[bulk + tid] = S.out[bulk + tid]; __threadfence(); }
+            } else {
+                for (int k = tid; k < len; k += kRowsThreads) dst[k] = S.out[k];
+                __threadfence();
+            }
+            if (tid == 0) pendFlag = &flags[t];
+        }
+        __syncthreads();                                       /* `out` tail reads are done; direct stores are fenced */
+    }
+    if (tid == 0) publishPending();
+}
+
 /* ---- ceiling of the rows kernel's skeleton (developer tool; bench.py --ceiling) ----
  * Same persistent structure -- one CTA of 1024 threads per SM, TMA bulk load of the compressed block into `in`, TMA bulk
  * store of 64 KB from `out` -- with the decode replaced by
@@ -1115,11 +1407,10 @@ int lz4k_debug_phase_cycles(unsigned long long* out8)   /* out8: 12 values (8 ph
     return (int)e;
 }
 
-static size_t ws_bytes(int64_t nBlocks, uint32_t markStride)
+static size_t ws_bytes_for(int64_t nBlocks, const int32_t* dstCapArr, int32_t dstCap)
 {
-    const size_t lst = (((size_t)nBlocks * 4 + 255) / 256) * 256;
-    const size_t mk = (((size_t)nBlocks * markStride * sizeof(uint32_t) + 255) / 256) * 256;
-    return 256 + 2 * lst + 3 * mk + 256;                      /* header | nSeq | slowList | marks | scratch (2 x marks) */
+    const bool wide = wide_batch(dstCapArr, dstCap);           /* the size that enables the tiles kernel */
+    return ws_bytes(nBlocks, mark_stride(dstCapArr, dstCap, wide), wide ? tiles_of(dstCap) : 0u);
 }
 
 size_t lz4k_decode_workspace_bytes(int64_t nBlocks)               /* any capacities (worst case: 32 KB of marks per block) */
@@ -1130,6 +1421,12 @@ size_t lz4k_decode_workspace_bytes(int64_t nBlocks)               /* any capacit
 size_t lz4k_decode_workspace_bytes_for(int64_t nBlocks, int perBlockCaps, int32_t dstCap)
 {
     static const int32_t one = 1;                                 /* any non-NULL pointer: "capacities are per block" */
+    return nBlocks < 0 ? 0 : ws_bytes_for(nBlocks, perBlockCaps ? &one : nullptr, dstCap);
+}
+
+size_t lz4k_decode_workspace_bytes_min(int64_t nBlocks, int perBlockCaps, int32_t dstCap)   /* smallest workspace a launch accepts */
+{
+    static const int32_t one = 1;
     return nBlocks < 0 ? 0 : ws_bytes(nBlocks, mark_stride(perBlockCaps ? &one : nullptr, dstCap));
 }
 
@@ -1138,6 +1435,7 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
     cudaStream_t s = (cudaStream_t)stream;
     if (a->nBlocks == 0) return 0;
     if (a->workspaceBytes < ws_bytes(a->nBlocks, mark_stride(a->dstCapArr, a->dstCap))) return (int)cudaErrorInvalidValue;
+    const bool wide = use_wide(a->dstCapArr, a->dstCap, a->nBlocks, a->workspaceBytes);
     static int sms = 0, scanImpl = -1;
     if (sms == 0) {
         int dev = 0, v = 148;
@@ -1146,6 +1444,7 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         /* opt in to the large dynamic shared memory (once; every device of a process runs the same kernels) */
         cudaError_t e = cudaFuncSetAttribute(lz4_expand_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(lz4_scan_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanParSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(lz4_expand_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
         if (e != cudaSuccess) return (int)e;
         const char* env = getenv("LZ4K_SCAN_IMPL");               /* developer A/B switch: "thread" | "par" | "split" */
         scanImpl = env ? (env[0] == 'p' ? 1 : env[0] == 's' ? 2 : 0) : -1;
@@ -1170,6 +1469,10 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
             const int64_t want = (int64_t)sms * 12;                   // 3 resident CTAs per SM, 4 rounds for balance
             const int64_t grid = a->nBlocks < want ? a->nBlocks : want;
             lz4_scan_par_kernel<<<(unsigned)grid, kScanLanes, sizeof(ScanParSmem), s>>>(*a);
+            if (wide) {                                                // tiles kernel: first sequence of every tile, flags cleared
+                lz4_tile_index_kernel<<<(unsigned)(a->nBlocks < (int64_t)sms * 8 ? a->nBlocks : (int64_t)sms * 8), 256, 0, s>>>(*a);
+                g_launches++;
+            }
         } else {
             const int threads = 128;
             const int64_t grid = (a->nBlocks + threads - 1) / threads;
@@ -1178,8 +1481,14 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         g_launches++;
     }
     if (phases & 2) {
-        int64_t grid = a->nBlocks < sms ? a->nBlocks : sms;          // persistent: one CTA per SM
-        lz4_expand_rows_kernel<<<(unsigned)grid, kRowsThreads, sizeof(RowsSmem), s>>>(*a);
+        if (wide) {                                                  // blocks above 64 KB: one CTA per 60 KB output tile
+            const int64_t units = a->nBlocks * (int64_t)tiles_of(a->dstCap);
+            const int64_t grid = units < sms ? units : sms;          // all CTAs resident: a tile may wait for its predecessor
+            lz4_expand_tiles_kernel<<<(unsigned)grid, kRowsThreads, sizeof(RowsSmem), s>>>(*a);
+        } else {
+            int64_t grid = a->nBlocks < sms ? a->nBlocks : sms;      // persistent: one CTA per SM
+            lz4_expand_rows_kernel<<<(unsigned)grid, kRowsThreads, sizeof(RowsSmem), s>>>(*a);
+        }
         g_launches++;
         const int threads = 128;                                     // 4 warps = 4 blocks per CTA, grid-stride over the slow list
         int64_t grid2 = (a->nBlocks * 32 + threads - 1) / threads;

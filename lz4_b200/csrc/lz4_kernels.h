@@ -44,6 +44,7 @@ typedef struct {
 size_t lz4k_decode_workspace_bytes(int64_t nBlocks);   /* any capacities */
 /* tighter: per-block capacity array (perBlockCaps != 0) or one capacity for every block */
 size_t lz4k_decode_workspace_bytes_for(int64_t nBlocks, int perBlockCaps, int32_t dstCap);
+size_t lz4k_decode_workspace_bytes_min(int64_t nBlocks, int perBlockCaps, int32_t dstCap);   /* without the wide marks of the tiles kernel */
 /* phases: bit 0 = scan (validate, sizes), bit 1 = expand (move bytes; needs a prior scan's outSize) */
 int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream);
 int lz4k_launch_encode(const lz4k_encode_args* a, void* stream);       /* byte-identical to LZ4_compress_fast */

@@ -80,6 +80,27 @@ RW_FN RwSeq rw_parse(const uint8_t* in, uint32_t mk, int k, bool last)
     return s;
 }
 
+/* The same from a WIDE mark (blocks above 64 KB: {token position, match start} as two words); `in` may be global memory */
+RW_FN RwSeq rw_parse_wide(const uint8_t* in, uint32_t tok, uint32_t mstart, bool last)
+{
+    RwSeq s;
+    const uint32_t t = in[tok];
+    int64_t pp = (int64_t)tok + 1;
+    int ll = (int)(t >> 4);
+    if (ll == 15) { uint32_t x; do { x = in[pp++]; ll += (int)x; } while (x == 255); }
+    s.ll = ll; s.ls = (int)pp; s.m = (int)mstart; s.op = (int)mstart - ll;
+    s.off = 0; s.mlen = 0;
+    if (!last) {
+        pp += ll;
+        s.off = (int)((uint32_t)in[pp] | ((uint32_t)in[pp + 1] << 8));
+        pp += 2;
+        int ml = (int)(t & 15u);
+        if (ml == 15) { uint32_t x; do { x = in[pp++]; ml += (int)x; } while (x == 255); }
+        s.mlen = ml + 4;
+    }
+    return s;
+}
+
 /* The runs of one match (m, off, len): calls f(start, delta) for each, in increasing start order.
  * delta is relative to the output position (source = p + delta); `zeroDelta0` is the delta that maps
  * output position 0 onto the always-zero cell (so position p needs zeroDelta0 - p). */
@@ -96,7 +117,32 @@ RW_FN void rw_match_runs(int m, int off, int len, int zeroDelta0, F f)
     /* [base, base + 2*period) reads `period` back; then pieces [base + period*2^t, base + period*2^(t+1))
      * read period*2^t back: always a multiple of the period and never before base - period */
     f(base, -period);
-    for (long long step = 2LL * period; step < rem; step *= 2) f(base + (int)step, -(int)step);
+    /* (no piece reads more than 65 535 back -- only matches of blocks above 64 KB get that far: the last piece then
+     * runs to the end of the match, still a multiple of the period back) */
+    for (long long step = 2LL * period; step < rem && step <= 65535; step *= 2) f(base + (int)step, -(int)step);
+}
+
+/* The runs of one sequence CLIPPED to the output tile [os, oe) of a block above 64 KB, as f(start - os, delta), in
+ * increasing start order.  Deltas keep the meaning "source = position + delta" in the tile's window (position counted
+ * from the tile start): a match run's delta is the same number as in block coordinates (a source before the tile start
+ * lies in an earlier tile = global memory); a literal run's delta is litBase + (ls - op), with litBase chosen by the
+ * caller so that the sum lands in a virtual range that means "byte ls + (p - op) of the compressed block";
+ * zeroDelta0 = what rw_match_runs needs for the always-zero cell, in the same convention. */
+template <class F>
+RW_FN void rw_tile_runs(const RwSeq& s, int os, int oe, uint32_t litBase, int zeroDelta0, F f)
+{
+    const int lo = s.op > os ? s.op : os, hi = (s.op + s.ll) < oe ? (s.op + s.ll) : oe;
+    if (hi > lo) f(lo - os, (int)(litBase + (uint32_t)(s.ls - s.op)));
+    if (s.mlen > 0 && s.m + s.mlen > os && s.m < oe) {
+        bool pend = false;                              /* the last piece that starts at or before the tile start covers it */
+        int pd = 0;
+        rw_match_runs(s.m, s.off, s.mlen, zeroDelta0, [&](int st, int d) {
+            if (st <= os) { pend = true; pd = d; return; }
+            if (pend) { f(0, pd); pend = false; }
+            if (st < oe) f(st - os, d);
+        });
+        if (pend) f(0, pd);
+    }
 }
 
 /* run index of output byte q: rows[r] = {bits of row r, (run starts before row r) - 1} */

@@ -11,6 +11,7 @@
 #ifndef LZ4_SCAN_CORE_H
 #define LZ4_SCAN_CORE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -68,7 +69,7 @@ template <bool G> SC_FN uint32_t ld32u(const uint8_t* p)
     return SC_FUNNEL_R(lo, hi, sh);
 }
 
-template <bool G> struct MemPtr {
+template <bool G, bool W = false> struct MemPtr {
     const uint8_t* p;
     SC_MFN uint32_t b(int64_t i) const { return ldb<G>(p + i); }
     SC_MFN uint32_t u16(int64_t i) const { return ld16<G>(p + i); }
@@ -77,6 +78,7 @@ template <bool G> struct MemPtr {
     SC_MFN void tick(int64_t) const { }
     SC_MFN void prefetch(int64_t i) const { if (G) SC_PREFETCH_L1(p + i); }
     static constexpr bool kPrefetch = G;
+    static constexpr bool kWide = W;            /* marks are two words per sequence (blocks above 64 KB): see MARK_COMMIT */
 };
 
 /* =============================================================================================
@@ -109,8 +111,13 @@ template <class M> SC_FN bool read_runlength(M& mem, int64_t& ip, int64_t ilimit
 constexpr int kMaxSeqFast = 8192;              // most sequences a block of the shared-memory expand kernel may have
 /* `markCap` = number of mark slots the caller reserved for this block (<= kMaxSeqFast); a block that can be
  * expanded from shared memory has at most capacity/4 + 1 sequences (every sequence but the last makes >= 4 bytes) */
+/* Blocks above 64 KB (decoded in 60 KB output tiles by lz4_expand_tiles_kernel) get WIDE marks: two words per sequence,
+ * {token position, match start}; the memory class of the walk says which (M::kWide). */
 #define MARK_COMMIT(tokpos, matchpos)                                                           \
-    do { if (marks && nseq < markCap) marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(matchpos) << 16); } while (0)
+    do { if (marks && nseq < markCap) {                                                         \
+        if (M::kWide) { marks[2 * (size_t)nseq] = (uint32_t)(tokpos); marks[2 * (size_t)nseq + 1] = (uint32_t)(matchpos); } \
+        else marks[nseq] = (uint32_t)(tokpos) | ((uint32_t)(matchpos) << 16);                   \
+    } } while (0)
 
 /* where the walk of one block stands between its two loops */
 struct ScanState {

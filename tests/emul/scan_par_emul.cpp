@@ -9,13 +9,12 @@ static int g_lanes = 128;
 extern "C" void scan_par_set_lanes(int nl) { g_lanes = nl; }
 
 // stats[0] = fix-up rounds, stats[1] = lane walks in the fix-up rounds, stats[2] = lane that finished the block
-extern "C" int scan_par_host(const uint8_t* src, int n, int cap, uint32_t* nSeqOut, uint32_t* marks, int* stats)
+template <class M>
+static int run_par(M& mem, int n, int cap, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap, int* stats)
 {
     const int nl = g_lanes;
-    const uint32_t markCap = (uint32_t)kMaxSeqFast;
     *nSeqOut = 0;
     stats[0] = stats[1] = 0; stats[2] = -1;
-    MemPtr<true> mem{src};
     if (cap < 64 || n < kSpMinBytes) return scan_block(mem, n, cap, nSeqOut, marks, markCap);   // lane 0, one-thread scan
     static SpShared S;
     static SpLane L[kSpMaxLanes];
@@ -41,6 +40,22 @@ extern "C" int scan_par_host(const uint8_t* src, int n, int cap, uint32_t* nSeqO
     stats[2] = first;
     *nSeqOut = S.nseq;
     return S.ret;
+}
+extern "C" int scan_par_host(const uint8_t* src, int n, int cap, uint32_t* nSeqOut, uint32_t* marks, int* stats)
+{
+    MemPtr<true> mem{src};
+    return run_par(mem, n, cap, nSeqOut, marks, (uint32_t)kMaxSeqFast, stats);
+}
+// blocks above 64 KB: wide marks (two words per sequence), parallel scan and one-thread scan
+extern "C" int scan_par_host_wide(const uint8_t* src, int n, int cap, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap, int* stats)
+{
+    MemPtr<true, true> mem{src};
+    return run_par(mem, n, cap, nSeqOut, marks, markCap, stats);
+}
+extern "C" int scan_thread_host_wide(const uint8_t* src, int n, int cap, uint32_t* nSeqOut, uint32_t* marks, uint32_t markCap)
+{
+    MemPtr<true, true> mem{src};
+    return scan_block(mem, n, cap, nSeqOut, marks, markCap);
 }
 
 // In-process differential fuzz: mutate a (valid) compressed block `iters` times, pick a capacity, and

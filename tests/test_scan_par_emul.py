@@ -153,3 +153,37 @@ def test_differential_fuzz_in_process(libs, lanes):
         total += n
         errors += ne.value
     assert total > 30000 // k and errors > 10000 // k
+
+
+def test_wide_marks_of_big_blocks(libs, lanes):
+    """Blocks above 64 KB get two-word marks {token position, match start} for the tiles kernel: the parallel scan and the
+    one-thread scan must write the same ones, on valid, truncated and corrupted blocks."""
+    _, v2 = libs
+    v2.scan_par_host_wide.restype = C.c_int
+    v2.scan_par_host_wide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_int)]
+    v2.scan_thread_host_wide.restype = C.c_int
+    v2.scan_thread_host_wide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]
+    gen = Reference() if have_reference() else Oracle()
+    rng = np.random.default_rng(lanes)
+    for proba, size, seed in ((0.5, 1 << 20, 1), (0.9, 300000, 2), (0.0, 150000, 3), (0.5, 4 << 20, 4)):
+        raw = bytes(gen.datagen(size, proba, seed))
+        _, comp = gen.compress(raw, 1)
+        variants = [(bytes(comp), size), (bytes(comp), size + 100), (bytes(comp), size - 1), (bytes(comp[:len(comp) // 2]), size)]
+        bad = bytearray(comp)
+        for pos in rng.integers(0, len(bad), 3):
+            bad[int(pos)] ^= 0x5A
+        variants.append((bytes(bad), size))
+        for blk, cap in variants:
+            mcap = cap // 4 + 2
+            buf = np.frombuffer(blk + b"\xEE" * 32, dtype=np.uint8).copy()
+            m1 = np.full(2 * mcap, 0xABABABAB, dtype=np.uint32)
+            m2 = np.full(2 * mcap, 0xABABABAB, dtype=np.uint32)
+            n1, n2 = C.c_uint32(0), C.c_uint32(0)
+            st = (C.c_int * 3)()
+            r1 = v2.scan_thread_host_wide(buf.ctypes.data, len(blk), cap, C.byref(n1), m1.ctypes.data, mcap)
+            r2 = v2.scan_par_host_wide(buf.ctypes.data, len(blk), cap, C.byref(n2), m2.ctypes.data, mcap, st)
+            assert r1 == r2 and n1.value == n2.value, (proba, size, cap, r1, r2, n1.value, n2.value)
+            if r1 > 0:
+                k = min(n1.value, mcap)
+                assert np.array_equal(m1[:2 * k], m2[:2 * k]), (proba, size, cap)
+                assert int(m1[2 * k - 1]) == r1                     # the last mark's second word = decoded size
