@@ -914,8 +914,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_tiles_kernel(lz4k_
 
         for (int k = tid; k < 2048; k += kRowsThreads) S.rows[k] = make_uint2(0u, 0u);
         __syncthreads();
-        /* ---- runs, pass 1 ---- */
-        for (int k = k0 + tid; k < k1; k += kRowsThreads) {
+        /* ---- runs, pass 1 (a thread's first sequences stay in registers for pass 2: parsing reads global memory) ---- */
+        RwSeq sq[kRowsCache];
+        #pragma unroll
+        for (int i = 0; i < kRowsCache; i++) {
+            const int k = k0 + tid + i * kRowsThreads;
+            if (k < k1) {
+                sq[i] = parse(k);
+                rw_tile_runs(sq[i], os, oe, litBase, zeroDelta0, [&](int st, int) { atomicOr(&S.rows[st >> 5].x, 1u << (st & 31)); });
+            }
+        }
+        for (int k = k0 + tid + kRowsCache * kRowsThreads; k < k1; k += kRowsThreads) {
             const RwSeq s = parse(k);
             rw_tile_runs(s, os, oe, litBase, zeroDelta0, [&](int st, int) { atomicOr(&S.rows[st >> 5].x, 1u << (st & 31)); });
         }
@@ -956,7 +965,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_tiles_kernel(lz4k_
             continue;
         }
         /* ---- runs, pass 2 ---- */
-        for (int k = k0 + tid; k < k1; k += kRowsThreads) {
+        #pragma unroll
+        for (int i = 0; i < kRowsCache; i++) {
+            const int k = k0 + tid + i * kRowsThreads;
+            if (k < k1) rw_tile_runs(sq[i], os, oe, litBase, zeroDelta0, [&](int st, int d) { S.tab[rw_rank(S.rows, (uint32_t)st)] = (uint32_t)d; });
+        }
+        for (int k = k0 + tid + kRowsCache * kRowsThreads; k < k1; k += kRowsThreads) {
             const RwSeq s = parse(k);
             rw_tile_runs(s, os, oe, litBase, zeroDelta0, [&](int st, int d) { S.tab[rw_rank(S.rows, (uint32_t)st)] = (uint32_t)d; });
         }

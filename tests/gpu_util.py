@@ -58,3 +58,33 @@ def decode_batch(blocks, caps):
         r = int(ret[i])
         res.append((r, out[o:o + max(r, 0)].tobytes()))
     return res
+
+
+def decode_batch_uniform(blocks, cap, wide=True):
+    """Run blocks through LZ4B200_decompress_blocks with ONE capacity for all of them (device API); wide=True gives the
+    workspace LZ4B200_decompress_workspace_bytes_for asks for (blocks above 64 KB: the tiles kernel), wide=False the
+    small one (blocks above 64 KB: the generic kernel).  Returns list of (ret, bytes)."""
+    from lz4_b200 import _lib
+    lib = _lib.load()
+    buf, offs, sizes = pack_host_blocks(blocks)
+    n = len(blocks)
+    stride = (cap + 64 + 15) // 16 * 16
+    d_buf, d_offs, d_sizes = to_dev(buf), to_dev(offs), to_dev(sizes)
+    d_out = torch.full((n * stride,), 0xA5, dtype=torch.uint8, device=dev())
+    d_ret = torch.zeros(n, dtype=torch.int32, device=dev())
+    nbytes = int(lib.LZ4B200_decompress_workspace_bytes_for(n, 0, cap)) if wide else int(lib.LZ4B200_decompress_workspace_bytes(n))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev())
+    rc = lib.LZ4B200_decompress_blocks(d_buf.data_ptr(), d_offs.data_ptr(), d_sizes.data_ptr(), d_out.data_ptr(),
+                                       None, stride, None, cap, d_ret.data_ptr(), n,
+                                       ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "decompress_blocks")
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    ret = d_ret.cpu().numpy()
+    res = []
+    for i in range(n):
+        o = i * stride
+        assert (out[o + cap:o + stride] == 0xA5).all(), "block %d wrote past its capacity" % i
+        r = int(ret[i])
+        res.append((r, out[o:o + max(r, 0)].tobytes()))
+    return res

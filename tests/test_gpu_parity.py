@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from gpu_util import decode_batch, dev, sha, to_dev
+from gpu_util import decode_batch, decode_batch_uniform, dev, sha, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -298,6 +298,48 @@ def test_large_blocks_4mb_incompressible_and_malformed(lib, oracle):
             assert out == eout
             good += 1
     assert good >= 8
+
+
+def test_big_blocks_in_tiles_vs_oracle(lib, oracle):
+    """Blocks above 64 KB with ONE capacity and the large workspace take the tiles kernel (60 KB output tiles, sources in
+    earlier tiles read from global memory): valid, incompressible, periodic, truncated and corrupted blocks of 70 KB .. 4 MB
+    -> the oracle's return value (incl. the negative error position) and bytes; the generic kernel (small workspace) must
+    agree."""
+    rng = np.random.default_rng(77)
+    TILE = 61440
+    def rep(seed, n):
+        return (seed * (n // len(seed) + 2))[:n]
+    noise = bytes(rng.integers(0, 256, 200000, dtype=np.uint8))
+    raws = [oracle.datagen(4 << 20, 0.5, 21).tobytes(), oracle.datagen(1 << 20, 0.9, 22).tobytes(),
+            oracle.datagen(300000, 0.0, 23).tobytes(), oracle.datagen(70001, 0.2, 24).tobytes(),
+            b"\0" * (1 << 20), rep(b"ab", 250000), rep(noise[:255], 300001), rep(noise[:TILE], 4 * TILE + 3),
+            rep(noise[:TILE + 1], 3 * TILE), rep(noise[:65535], 262144),
+            noise + noise[:150000] + b"\0" * 130000 + noise[100:90000]]
+    for group_cap in (None, 64):                                # exact capacity per block / 64 bytes of slack
+        for raw in raws:
+            _, c = oracle.compress(raw, 1)
+            n = len(raw)
+            cap = n if group_cap is None else n + group_cap
+            blocks = [c, c[:-1], c[:len(c) // 2], c + b"\0"]
+            for _ in range(2):
+                b = bytearray(c)
+                for _ in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+                blocks.append(bytes(b))
+            res = decode_batch_uniform(blocks, cap, wide=True)
+            res_small = decode_batch_uniform(blocks, cap, wide=False)
+            for blk, (ret, out), (ret2, out2) in zip(blocks, res, res_small):
+                eret, eout = oracle.decompress(blk, cap)
+                assert ret == eret and ret2 == eret, (n, cap, len(blk), ret, ret2, eret)
+                if ret >= 0:
+                    assert out == eout and out2 == eout, (n, cap, len(blk))
+            assert res[0][0] == n
+    # many big blocks at once: tile-major units across blocks, ragged sizes under one capacity
+    raws = [oracle.datagen(int(rng.integers(70000, 600000)), float(rng.choice([0.2, 0.5, 0.9])), 100 + i).tobytes() for i in range(40)]
+    blocks = [oracle.compress(r, 1)[1] for r in raws]
+    res = decode_batch_uniform(blocks, 600000, wide=True)
+    for r, (ret, out) in zip(raws, res):
+        assert ret == len(r) and out == r
 
 
 def test_host_buffer_batch_calls(lib, oracle):
