@@ -534,7 +534,7 @@ def run_ours(args):
         if abs(args.proba - tj.get("proba", 0.5)) < 1e-9 and BLOCK == tj.get("block_bytes", 65536):
             traffic = int(tj["expand_dram_bytes_per_block"] * n_blocks)
             step_traffic = int((tj["expand_dram_bytes_per_block"] + tj["scan_dram_bytes_per_block"]) * n_blocks)
-            traffic_src = tj.get("source")
+            traffic_src = "profiles/traffic.json: " + "; ".join("%s = %s" % kv for kv in sorted(tj.get("sources", {}).items()) if kv[0] in ("expand", "scan"))
     except (OSError, ValueError, KeyError):
         pass
     config = workload_config(n_blocks, args.gib, args.proba, args.accel, total / comp_bytes, world)

@@ -1,0 +1,46 @@
+"""Developer check: the parallel compressor must give the same bytes whatever the destination layout / capacity.
+Runs the same 8 blocks into differently laid out slot buffers and reports sizes, first differing byte, oracle decode."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from lz4_b200 import batch  # noqa: E402
+from oracle.pyoracle import Oracle  # noqa: E402
+
+BS = 65536
+orc = Oracle()
+d = orc.datagen_mt(8 * BS, 1 << 20, 0.5, 21)
+src = torch.from_numpy(d).cuda()
+
+
+def run(cap=None, extra=0, fill=None):
+    if cap is None:
+        slots, sizes, stride = batch.compress_blocks(src, BS, 1, mode="parallel")
+    else:
+        stride = (cap + 15) // 16 * 16 + extra
+        slots = torch.full((8 * stride,), 0xA5 if fill is None else fill, dtype=torch.uint8, device="cuda")
+        sizes = torch.zeros(8, dtype=torch.int32, device="cuda")
+        batch.compress_blocks(src, BS, 1, slots=slots, slot_stride=stride, slot_capacity=cap, out_sizes=sizes, mode="parallel")
+    torch.cuda.synchronize()
+    return slots.cpu().numpy(), sizes.cpu().numpy(), stride
+
+
+ref_h, ref_s, ref_st = run()
+print("run 0 sizes", ref_s.tolist())
+cfgs = [(None, 0), (int(ref_s.max()), 64), (int(ref_s.max()), 64), (int(ref_s.max()) + 5, 80), (70000, 16), (None, 0)]
+for n, (cap, extra) in enumerate(cfgs, 1):
+    h, s, st = run(cap, extra)
+    bad = []
+    for i in range(8):
+        a = ref_h[i * ref_st:i * ref_st + ref_s[i]]
+        b = h[i * st:i * st + s[i]]
+        ok_dec = orc.decompress(b.tobytes(), BS) == (BS, d[i * BS:(i + 1) * BS].tobytes()) if s[i] > 0 else None
+        if s[i] != ref_s[i] or not np.array_equal(a, b):
+            m = min(len(a), len(b))
+            diff = np.nonzero(a[:m] != b[:m])[0]
+            bad.append((i, int(ref_s[i]), int(s[i]), int(diff[0]) if len(diff) else m, ok_dec))
+    print("run %d cap %s stride %d: %s" % (n, cap, st, "identical" if not bad else "DIFFERS (block, size0, size, first diff, decodes) %s" % bad))
