@@ -68,6 +68,11 @@ int LZ4B200_peer_copy_async(void* d_dstPeer, int peerDevice, const void* d_src, 
     return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "cudaMemcpyAsync (peer)");
 }
 
+/* not part of the public header: developer hook used by tests/perf/enc_determinism.py */
+__attribute__((visibility("default"))) int LZ4B200_debug_poison_smem(uint32_t pattern, int lo, int hi, void* stream)
+{
+    return lz4k_debug_poison_smem(pattern, lo, hi, stream);
+}
 /* not part of the public header: developer hook used by bench.py --ceiling (the rows kernel's skeleton without the decode) */
 __attribute__((visibility("default"))) int LZ4B200_debug_ceiling(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
                                                                   void* d_dst, int64_t dstStride, int64_t nBlocks, int mode, void* stream)

@@ -1528,6 +1528,27 @@ int lz4k_launch_encode(const lz4k_encode_args* a, void* stream)
     return (int)cudaGetLastError();
 }
 
+/* developer tool: fill bytes [lo, hi) of every CTA's dynamic shared memory (parallel compressor layout) with a pattern, so
+ * that a later launch that read shared memory it never wrote would show it (tests/perf/enc_determinism.py) */
+__global__ void __launch_bounds__(kEpThreads, 2) lz4_poison_smem_kernel(uint32_t pattern, int lo, int hi)
+{
+    extern __shared__ __align__(16) uint8_t smemRaw[];
+    for (int i = lo + (int)threadIdx.x; i < hi; i += kEpThreads) smemRaw[i] = (uint8_t)(pattern >> ((i & 3) * 8));
+    __syncthreads();
+    if (smemRaw[lo] == 1 && pattern == 0x12345678u && hi == -1) smemRaw[0] = 0;   /* keep the stores */
+}
+int lz4k_debug_poison_smem(uint32_t pattern, int lo, int hi, void* stream)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(lz4_poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncParSmem));
+    if (e != cudaSuccess) return (int)e;
+    if (hi > (int)sizeof(EncParSmem)) hi = (int)sizeof(EncParSmem);
+    lz4_poison_smem_kernel<<<2 * sms, kEpThreads, sizeof(EncParSmem), (cudaStream_t)stream>>>(pattern, lo, hi);
+    return (int)cudaGetLastError();
+}
+
 int lz4k_launch_ceiling(const lz4k_decode_args* a, int mode, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;

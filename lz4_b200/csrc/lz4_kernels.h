@@ -55,6 +55,7 @@ int lz4k_launch_pack(const uint8_t* slots, int64_t slotStride, const int32_t* si
 int lz4k_launch_pack_frame(const uint8_t* slots, int64_t slotStride, const int32_t* sizes, const uint8_t* src, int64_t srcStride,
                            int32_t blockSize, int32_t lastSize, int64_t nBlocks, uint8_t* packed, int64_t* outOff, void* stream);
 uint64_t lz4k_launch_count(void);
+int lz4k_debug_poison_smem(uint32_t pattern, int lo, int hi, void* stream);   /* developer tool */
 int lz4k_launch_ceiling(const lz4k_decode_args* a, int mode, void* stream);   /* developer tool: skeleton of the rows kernel without the decode */
 int lz4k_debug_phase_cycles(unsigned long long* out8);
 

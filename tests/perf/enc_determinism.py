@@ -44,3 +44,20 @@ for n, (cap, extra) in enumerate(cfgs, 1):
             diff = np.nonzero(a[:m] != b[:m])[0]
             bad.append((i, int(ref_s[i]), int(s[i]), int(diff[0]) if len(diff) else m, ok_dec))
     print("run %d cap %s stride %d: %s" % (n, cap, st, "identical" if not bad else "DIFFERS (block, size0, size, first diff, decodes) %s" % bad))
+
+# ---- does the result depend on shared memory the kernel never wrote?  poison regions of it before a run ----
+import ctypes as C  # noqa: E402
+from lz4_b200 import _lib  # noqa: E402
+lib = _lib.load()
+lib.LZ4B200_debug_poison_smem.restype = C.c_int
+lib.LZ4B200_debug_poison_smem.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+regions = {"all": (0, 1 << 20), "pad": (0, 16), "src": (16, 65616), "src tail": (16 + 65536, 65616), "TT": (65616, 98384),
+           "stage": (98384, 107088), "small arrays": (107088, 1 << 20)}
+for name, (lo, hi) in regions.items():
+    outs = []
+    for pattern in (0x00000000, 0xFFFFFFFF, 0x5A17C3E9):
+        assert lib.LZ4B200_debug_poison_smem(pattern, lo, hi, torch.cuda.current_stream().cuda_stream) == 0
+        h, s, st = run()
+        outs.append((s.tolist(), [int(np.bitwise_xor.reduce(h[i * st:i * st + s[i]].astype(np.uint8))) for i in range(8)]))
+    same = all(o == outs[0] for o in outs)
+    print("poison %-12s -> %s" % (name, "same result" if same else "RESULT DEPENDS ON IT: %s" % [o[0] for o in outs]))
