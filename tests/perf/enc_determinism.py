@@ -45,6 +45,23 @@ for n, (cap, extra) in enumerate(cfgs, 1):
             bad.append((i, int(ref_s[i]), int(s[i]), int(diff[0]) if len(diff) else m, ok_dec))
     print("run %d cap %s stride %d: %s" % (n, cap, st, "identical" if not bad else "DIFFERS (block, size0, size, first diff, decodes) %s" % bad))
 
+# ---- the capacity ladder of test_limited_output_and_never_past_capacity ----
+for cap in (int(ref_s.max()), int(ref_s.max()) - 1, int(ref_s.min()), int(ref_s.min()) - 1, 1000, 1):
+    h, s, st = run(cap, 64)
+    rep = []
+    for i in range(8):
+        if ref_s[i] <= cap:
+            a = ref_h[i * ref_st:i * ref_st + ref_s[i]]
+            b = h[i * st:i * st + max(int(s[i]), 0)]
+            if s[i] != ref_s[i] or not np.array_equal(a, b):
+                m = min(len(a), len(b))
+                diff = np.nonzero(a[:m] != b[:m])[0]
+                dec = orc.decompress(b.tobytes(), BS) == (BS, d[i * BS:(i + 1) * BS].tobytes()) if s[i] > 0 else None
+                rep.append((i, int(ref_s[i]), int(s[i]), int(diff[0]) if len(diff) else m, int(len(diff)), dec))
+        elif s[i] != 0:
+            rep.append((i, "should not fit", int(s[i])))
+    print("cap %d: %s" % (cap, "ok" if not rep else "BAD (block, size0, size, first diff, #diff, decodes) %s" % rep))
+sys.exit(0)
 # ---- does the result depend on shared memory the kernel never wrote?  poison regions of it before a run ----
 import ctypes as C  # noqa: E402
 from lz4_b200 import _lib  # noqa: E402
