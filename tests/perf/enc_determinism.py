@@ -31,6 +31,17 @@ def run(cap=None, extra=0, fill=None):
 
 ref_h, ref_s, ref_st = run()
 print("run 0 sizes", ref_s.tolist())
+for i in range(8):
+    blk = ref_h[i * ref_st:i * ref_st + ref_s[i]].tobytes()
+    ret, out = orc.decompress(blk, BS)
+    want = d[i * BS:(i + 1) * BS].tobytes()
+    if (ret, out) != (BS, want):
+        bad = [k for k in range(min(len(out), BS)) if out[k] != want[k]]
+        print("run 0 block %d DOES NOT DECODE to the input: ret %d, %d wrong bytes, first at %s, last at %s" %
+              (i, ret, len(bad), bad[:8], bad[-3:]))
+    else:
+        print("run 0 block %d decodes" % i)
+np.save(os.path.join(ROOT, "gpurun_out", "enc_det_%s.npy" % os.environ.get("TAG", "plain")), np.concatenate([ref_s.astype(np.uint8).view(np.uint8), ref_h]))
 cfgs = [(None, 0), (int(ref_s.max()), 64), (int(ref_s.max()), 64), (int(ref_s.max()) + 5, 80), (70000, 16), (None, 0)]
 for n, (cap, extra) in enumerate(cfgs, 1):
     h, s, st = run(cap, extra)
