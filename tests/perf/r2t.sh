@@ -1,7 +1,9 @@
 #!/bin/bash
+# bisect the parallel compressor's sanitizer-only corruption over its history (current tree, historical lz4_encode_par.cuh)
 set -u
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
-echo "== memcheck"; TAG=memcheck timeout 600 compute-sanitizer --tool memcheck python tests/perf/enc_determinism.py 2>&1 | grep -v "^=========$" | head -14 | cut -c1-400
-echo "== plain"; TAG=plain timeout 300 python tests/perf/enc_determinism.py 2>&1 | head -12 | cut -c1-400
-echo "== racecheck"; TAG=racecheck timeout 600 compute-sanitizer --tool racecheck python tests/perf/enc_determinism.py 2>&1 | grep -v "^=========$" | head -14 | cut -c1-400
+for c in 73476e5 6d914c5 a1a4a21 200112d; do
+  echo "== encoder of $c under memcheck"
+  LZ4_B200_LIBRARY=$PWD/lz4_b200/build/liblz4_b200_bis_$c.so TAG=bis timeout 400 compute-sanitizer --tool memcheck python tests/perf/enc_determinism.py 2>&1 | grep -E "run 0 sizes|DOES NOT|DIFFERS|ERROR SUMMARY|Error" | head -8 | cut -c1-300
+done
