@@ -60,7 +60,7 @@ struct EncParSmem {
     int warpFirst[kEpWarps][2];                      /* emit: {start, output offset - position of its literals (relative to the warp's output)} of the warp's first sequence */
     int warpLast[kEpWarps];                          /* chain scan: end of the last match selected in each warp, or -1 */
     uint32_t warpSum[kEpWarps];
-    uint32_t E, O, fail;
+    uint32_t E, O, fail, anyMoved;
     alignas(8) uint64_t mbar;
 };
 static_assert(sizeof(EncParSmem) <= (232448 - 2048) / 2, "two CTAs of the parallel compressor must fit one SM");
@@ -242,8 +242,14 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                     }
                     exitE = e;
                 }
+#ifdef LZ4K_EXTRA_SYNCWARP
+                __syncwarp();
+#endif
                 unsigned pend = __ballot_sync(kFull, pendK >= 0);
                 while (pend) {
+#ifdef LZ4K_EXTRA_SYNCWARP
+                    __syncwarp();
+#endif
                     const int sl = __ffs(pend) - 1;
                     pend &= pend - 1;
                     int jp = 0; uint32_t jc = 0;
@@ -253,6 +259,9 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                     const int limit = matchlimit - jp;
                     int L = kEpSolo;
                     for (;;) {
+#ifdef LZ4K_EXTRA_SYNCWARP
+                        __syncwarp();
+#endif
                         const int o = L + 4 * lane;
                         const bool stop = o >= limit;                              /* at or past the allowed end: counts as a mismatch at o */
                         uint32_t x = 0;
@@ -311,7 +320,17 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                 const int w0 = c0 + kEpPer * 32 * warp;                  /* the warp's first position */
                 const bool moved = max(entry - w0, 0) != max(warpEntry - w0, 0);
                 warpEntry = entry;
+#ifdef LZ4K_NO_BAR_RED
+                /* experiment: the same decision through a shared flag and plain barriers */
+                if (tid == 0) S.anyMoved = 0;
+                __syncthreads();
+                if (moved) S.anyMoved = 1;
+                __syncthreads();
+                if (!S.anyMoved) break;
+                __syncthreads();
+#else
                 if (!__syncthreads_or(moved ? 1 : 0)) break;
+#endif
 #ifdef LZ4K_PHASE_TIMING
                 statRounds++;
 #endif
