@@ -232,7 +232,11 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                                 const int limit = matchlimit - p;
                                 c = ep_candidate_of_kind(S, src, head, p, c0, (uint32_t)(kinds >> (4 * rel)) & 15u);
                                 L = ep_extend(src, head, p, c, min(limit, kEpSolo));
+#ifdef LZ4K_NO_COOP
+                                if (L >= kEpSolo && L < limit) L = ep_extend(src, head, p, c, limit);      /* experiment: the lane finishes alone */
+#else
                                 if (L >= kEpSolo && L < limit) pendK = k;
+#endif
                             }
                             sPos[k] = p; sCand[k] = c; sLen[k] = L; sLit[k] = e;
                             nSel = k + 1;
@@ -264,8 +268,13 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
 #endif
                         const int o = L + 4 * lane;
                         const bool stop = o >= limit;                              /* at or past the allowed end: counts as a mismatch at o */
+#ifdef LZ4K_COOP_BRANCHFREE
+                        const uint32_t oc = stop ? 0u : (uint32_t)o;             /* a stopped lane compares the match's first word with itself */
+                        const uint32_t x = ep_ld32(src, (uint32_t)(head + jp) + oc) ^ ep_ld32(src, (uint32_t)head + jc + oc);
+#else
                         uint32_t x = 0;
                         if (!stop) x = ep_ld32(src, (uint32_t)(head + jp + o)) ^ ep_ld32(src, (uint32_t)head + jc + (uint32_t)o);
+#endif
                         const unsigned mm = __ballot_sync(kFull, stop || x != 0u);
                         if (mm) {
                             const int f = __ffs(mm) - 1;
