@@ -357,7 +357,19 @@ def run_ours(args):
         batch.decompress_blocks(packed, offs[lo:hi], csizes[lo:hi], BLOCK, out=out[lo * BLOCK:hi * BLOCK],
                                 out_sizes=rets[lo:hi], workspace=ws, phases=phases)
 
-    peer = ldist.PeerFrame(full) if world > 1 and args.exchange == "peer" else None
+    peer, exchange = None, args.exchange
+    if world > 1 and exchange == "peer":
+        # every rank must take the same path: agree on whether the peers' frames could be mapped (CUDA IPC + peer access)
+        try:
+            peer = ldist.PeerFrame(full)
+            ok = 1
+        except Exception as e:                     # noqa: BLE001 -- any failure means "use NCCL instead", on every rank
+            sys.stderr.write("rank %d: peer-memory exchange unavailable (%s); falling back to NCCL send/recv\n" % (rank, e))
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            peer, exchange = None, "nccl"
 
     def step():
         """one pass of the hot path over this rank's batch; N > 1: + the exchange of the decoded shards, overlapped"""
@@ -570,10 +582,10 @@ def run_ours(args):
     }
     if world > 1:
         how = ("copy-engine pushes into the peers' frames over NVLink peer memory (CUDA IPC), one stream per peer"
-               if args.exchange == "peer" else "grouped NCCL send/recv per chunk")
+               if exchange == "peer" else "grouped NCCL send/recv per chunk")
         line["multi_gpu"] = {"value_includes": "decode + exchange of the decoded shards (%s; %d chunks, exchange of chunk k "
                                                "overlaps the decode of chunk k+1)" % (how, args.chunks),
-                             "exchange": args.exchange,
+                             "exchange": exchange,
                              "per_rank_ms_per_step": per_rank_ms,
                              "codec_only": {"ms_per_step_max_over_ranks": round(codec_ms_max, 4),
                                             "GBps": round(world * total / (codec_ms_max * 1e-3) / GB, 3)},

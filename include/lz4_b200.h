@@ -185,7 +185,8 @@ LZ4B200_API int LZ4B200_pack_frame_blocks(const void* d_slots, int64_t slotStrid
  * Multi-GPU reassembly (the ordered-writer role of programs/lz4io.c:594-635 when every GPU decodes a shard of a frame):
  * enqueue on `stream` the copy of `bytes` device bytes from d_src (current device) to d_dstPeer, memory of device
  * `peerDevice` that is mapped into this process (cudaIpcOpenMemHandle / a same-process allocation).  Peer access is
- * enabled on first use; the copy runs on a copy engine over NVLink and takes no SM from the codec kernels.
+ * enabled on first use (a call with bytes == 0 only does that: a probe); the copy runs on a copy engine over NVLink and
+ * takes no SM from the codec kernels.
  * Returns LZ4B200_OK, LZ4B200_ERR_ARG (the devices cannot reach each other directly) or LZ4B200_ERR_CUDA.
  */
 LZ4B200_API int LZ4B200_peer_copy_async(void* d_dstPeer, int peerDevice, const void* d_src, size_t bytes, void* stream);

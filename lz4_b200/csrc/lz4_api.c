@@ -49,8 +49,7 @@ int LZ4B200_peer_copy_async(void* d_dstPeer, int peerDevice, const void* d_src, 
     static unsigned char enabled[64][64];
     int cur = 0;
     cudaError_t e;
-    if (bytes == 0) return LZ4B200_OK;
-    if (!d_dstPeer || !d_src || peerDevice < 0 || peerDevice >= 64) return LZ4B200_ERR_ARG;
+    if (peerDevice < 0 || peerDevice >= 64 || (bytes && (!d_dstPeer || !d_src))) return LZ4B200_ERR_ARG;
     e = cudaGetDevice(&cur);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
     if (cur >= 64) return LZ4B200_ERR_ARG;
@@ -64,6 +63,7 @@ int LZ4B200_peer_copy_async(void* d_dstPeer, int peerDevice, const void* d_src, 
         else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
         enabled[cur][peerDevice] = 1;
     }
+    if (bytes == 0) return LZ4B200_OK;                   /* (a zero-byte call is the probe: peer access is enabled or refused) */
     e = cudaMemcpyAsync(d_dstPeer, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
     return e == cudaSuccess ? LZ4B200_OK : cuda_fail(e, "cudaMemcpyAsync (peer)");
 }

@@ -26,10 +26,11 @@
  *           once: every lane walks its 16 positions as if the chain entered at its first position, a CTA-wide
  *           "last valid value" scan hands every lane the end of the last match selected before it, lanes whose
  *           search would start elsewhere walk again, until nothing changes.  Only SELECTED positions extend their
- *           match, so the total comparison work is O(block size).
- *   emit    backward extension (lz4.c:1107-1109), sizes, CTA-wide exclusive sum; a window's output is assembled in
- *           shared memory and written out as consecutive bytes (scattered byte stores to HBM cost a transaction
- *           each); literal runs above 32 bytes are copied by a whole warp.
+ *           match (4 bytes per step for the first 32, then 8), so the total comparison work is O(block size).
+ *   emit    backward extension (lz4.c:1107-1109), sizes, CTA-wide exclusive sum; every lane writes the headers of its
+ *           sequences, the literals are copied position-parallel (every lane stores those of its 16 positions that are
+ *           literals); a window's output is assembled in shared memory and written out in aligned 16-byte pieces
+ *           (scattered byte stores to HBM cost a transaction each).
  *   insert  the window's positions enter the low halves (atomicMax, after the high halves are cleared).
  *
  * The end-of-block rules of the format are the reference's: no match starts after n-12, the last 5 bytes
@@ -60,7 +61,7 @@ struct EncParSmem {
     int warpFirst[kEpWarps][2];                      /* emit: {start, output offset - position of its literals (relative to the warp's output)} of the warp's first sequence */
     int warpLast[kEpWarps];                          /* chain scan: end of the last match selected in each warp, or -1 */
     uint32_t warpSum[kEpWarps];
-    uint32_t E, O, fail, anyMoved;
+    uint32_t E, O, fail;
     alignas(8) uint64_t mbar;
 };
 static_assert(sizeof(EncParSmem) <= (232448 - 2048) / 2, "two CTAs of the parallel compressor must fit one SM");
@@ -132,6 +133,26 @@ __device__ __forceinline__ int ep_extend(const uint8_t* src, int head, int p, ui
         a0 = a1; b0 = b1; wa++; wb++; L += 4;
     }
     return L > limit ? limit : L;
+}
+
+/* The same from a known common length L0 (a multiple of 4 is not required) up to `limit`: 8 bytes per step.
+ * A lane finishes a long match ALONE.  Round 2 also measured a warp-cooperative finish (128 bytes per step through ballots:
+ * +12 % on P50, +20 % on P90) -- correct on the hardware, but under compute-sanitizer the instrumented loads inside its loop
+ * split the warp while the compiler, having proved the warp converged, emits bare VOTE / SHFL and a loop counter in a
+ * uniform register: the ballots then see partial warps and matches come out too long.  A kernel that cannot be checked
+ * by the sanitizer is not worth 12 %; profiles/sanitizer_r02.txt, DESIGN.md 5.1. */
+__device__ __forceinline__ int ep_extend_from(const uint8_t* src, int head, int p, uint32_t c, int L0, int limit)
+{
+    int L = L0;
+    while (L + 8 <= limit) {
+        const uint32_t x0 = ep_ld32(src, (uint32_t)(head + p + L)) ^ ep_ld32(src, (uint32_t)head + c + (uint32_t)L);
+        const uint32_t x1 = ep_ld32(src, (uint32_t)(head + p + L + 4)) ^ ep_ld32(src, (uint32_t)head + c + (uint32_t)L + 4u);
+        if (x0) return L + ((__ffs(x0) - 1) >> 3);
+        if (x1) return L + 4 + ((__ffs(x1) - 1) >> 3);
+        L += 8;
+    }
+    while (L < limit && src[head + p + L] == src[(uint32_t)head + c + (uint32_t)L]) L++;
+    return L;
 }
 
 __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_encode_args a)
@@ -212,11 +233,10 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
             uint32_t sCand[kEpMaxSel];
             int cacheP = -1, cacheL = 0;                               /* the last long match this lane extended (walks repeat) */
             uint32_t cacheC = 0;
-            /* One walk of every lane that `go`es: the lane's positions from the chain position e.  A match is compared by its lane
-             * alone for kEpSolo bytes; one that is still running then is the lane's LAST selection (it covers the rest of the lane's
-             * 16 positions) and is finished by the whole warp, 128 bytes per step -- a 500-byte match costs 4 steps instead of 120. */
+            /* One walk of every lane that `go`es: the lane's positions from the chain position e.  A match of kEpSolo bytes or more
+             * is the lane's LAST selection (it covers the rest of the lane's 16 positions); its length is remembered, because the
+             * lane may walk again from another entry and meet it again. */
             auto walk = [&](bool go, int e) {
-                int pendK = -1;
                 if (go) {
                     nSel = 0;
                     int rel = max(e - p0, 0);
@@ -232,11 +252,10 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                                 const int limit = matchlimit - p;
                                 c = ep_candidate_of_kind(S, src, head, p, c0, (uint32_t)(kinds >> (4 * rel)) & 15u);
                                 L = ep_extend(src, head, p, c, min(limit, kEpSolo));
-#ifdef LZ4K_NO_COOP
-                                if (L >= kEpSolo && L < limit) L = ep_extend(src, head, p, c, limit);      /* experiment: the lane finishes alone */
-#else
-                                if (L >= kEpSolo && L < limit) pendK = k;
-#endif
+                                if (L >= kEpSolo && L < limit) {                 /* a long match: on, alone (see ep_extend_from), and remembered */
+                                    L = ep_extend_from(src, head, p, c, L, limit);
+                                    cacheP = p; cacheC = c; cacheL = L;
+                                }
                             }
                             sPos[k] = p; sCand[k] = c; sLen[k] = L; sLit[k] = e;
                             nSel = k + 1;
@@ -245,52 +264,6 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                         }
                     }
                     exitE = e;
-                }
-#ifdef LZ4K_EXTRA_SYNCWARP
-                __syncwarp();
-#endif
-                unsigned pend = __ballot_sync(kFull, pendK >= 0);
-                while (pend) {
-#ifdef LZ4K_EXTRA_SYNCWARP
-                    __syncwarp();
-#endif
-                    const int sl = __ffs(pend) - 1;
-                    pend &= pend - 1;
-                    int jp = 0; uint32_t jc = 0;
-                    #pragma unroll
-                    for (int k = 0; k < kEpMaxSel; k++) if (k == pendK) { jp = sPos[k]; jc = sCand[k]; }
-                    jp = __shfl_sync(kFull, jp, sl); jc = __shfl_sync(kFull, jc, sl);
-                    const int limit = matchlimit - jp;
-                    int L = kEpSolo;
-                    for (;;) {
-#ifdef LZ4K_EXTRA_SYNCWARP
-                        __syncwarp();
-#endif
-                        const int o = L + 4 * lane;
-                        const bool stop = o >= limit;                              /* at or past the allowed end: counts as a mismatch at o */
-#ifdef LZ4K_COOP_BRANCHFREE
-                        const uint32_t oc = stop ? 0u : (uint32_t)o;             /* a stopped lane compares the match's first word with itself */
-                        const uint32_t x = ep_ld32(src, (uint32_t)(head + jp) + oc) ^ ep_ld32(src, (uint32_t)head + jc + oc);
-#else
-                        uint32_t x = 0;
-                        if (!stop) x = ep_ld32(src, (uint32_t)(head + jp + o)) ^ ep_ld32(src, (uint32_t)head + jc + (uint32_t)o);
-#endif
-                        const unsigned mm = __ballot_sync(kFull, stop || x != 0u);
-                        if (mm) {
-                            const int f = __ffs(mm) - 1;
-                            const uint32_t xf = __shfl_sync(kFull, x, f);
-                            const bool sf = __shfl_sync(kFull, (int)stop, f) != 0;
-                            L = L + 4 * f + (sf ? 0 : ((__ffs(xf) - 1) >> 3));
-                            break;
-                        }
-                        L += 128;
-                    }
-                    if (L > limit) L = limit;
-                    if (lane == sl) {
-                        #pragma unroll
-                        for (int k = 0; k < kEpMaxSel; k++) if (k == pendK) { sLen[k] = L; cacheP = sPos[k]; cacheC = sCand[k]; cacheL = L; }
-                        exitE = jp + L;
-                    }
                 }
             };
             walk(true, eCur);
@@ -329,17 +302,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                 const int w0 = c0 + kEpPer * 32 * warp;                  /* the warp's first position */
                 const bool moved = max(entry - w0, 0) != max(warpEntry - w0, 0);
                 warpEntry = entry;
-#ifdef LZ4K_NO_BAR_RED
-                /* experiment: the same decision through a shared flag and plain barriers */
-                if (tid == 0) S.anyMoved = 0;
-                __syncthreads();
-                if (moved) S.anyMoved = 1;
-                __syncthreads();
-                if (!S.anyMoved) break;
-                __syncthreads();
-#else
                 if (!__syncthreads_or(moved ? 1 : 0)) break;
-#endif
 #ifdef LZ4K_PHASE_TIMING
                 statRounds++;
 #endif

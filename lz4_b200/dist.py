@@ -73,12 +73,23 @@ class PeerFrame:
         handles = [None] * self.world
         dist.all_gather_object(handles, reduce_tensor(full), group=group)
         self.peers = [None] * self.world                       # peers[r] = rank r's frame, writable from here
-        for r, (fn, fargs) in enumerate(handles):
-            if r != self.rank:
-                self.peers[r] = fn(*fargs)
         self.streams = [torch.cuda.Stream(device=full.device) for _ in range(self.world - 1)]
         self.token = torch.zeros(1, dtype=torch.int32, device=full.device)
-        dist.barrier(group)                                    # nobody pushes before everybody has mapped
+        err = None
+        try:                                                   # (no collective inside: a rank that fails must not strand the others)
+            for r, (fn, fargs) in enumerate(handles):
+                if r != self.rank:
+                    self.peers[r] = fn(*fargs)
+                    rc = self.lib.LZ4B200_peer_copy_async(None, self.peers[r].device.index, None, 0, None)   # probe: enables peer access
+                    if rc != 0:
+                        raise RuntimeError("device %d cannot reach device %d directly (LZ4B200_peer_copy_async: %d)"
+                                           % (full.device.index, self.peers[r].device.index, rc))
+        except Exception as e:                                 # noqa: BLE001
+            err = e
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=full.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # everybody has mapped everybody, or nobody uses the mapping
+        if int(ok.item()) == 0:
+            raise RuntimeError("peer mapping failed on at least one rank%s" % (": %s" % err if err else ""))
 
     def push(self, lo, hi):
         """Enqueue the copy of full[lo:hi] (this rank's freshly decoded bytes, ordered after the current stream's work so
