@@ -989,6 +989,30 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_tiles_kernel(lz4k_
                 if ((wv + 1) * kWave <= len) tiles_resolve<true>(sa, p0, outS + (uint32_t)(wv * kWave), 0xFFFFFFFFu, outS, rowsS, tabS, le);
                 else tiles_resolve<false>(sa, p0, outS + (uint32_t)(wv * kWave), (uint32_t)len, outS, rowsS, tabS, le);
             };
+#ifdef LZ4K_WAVE_BARSYNC
+            /* debug build (see lz4_expand_rows_kernel): a plain CTA barrier between the waves, for compute-sanitizer's racecheck */
+            for (int wv = 0; wv < nWaves; wv++) {
+                resolve(wv);
+                const uint32_t p0 = (uint32_t)(wv * kWave + tid);
+                const uint32_t lim = ((wv + 1) * kWave <= len) ? 0xFFFFFFFFu : (uint32_t)len;
+                uint32_t v[kRowsRpt];
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++) {
+                    const uint32_t x = sa[r];
+                    v[r] = 0u;
+                    if (p0 + (uint32_t)(r * kRowsThreads) < lim) {
+                        if (x >= kLitBase) v[r] = (x == kZeroV) ? 0u : (uint32_t)__ldg(src + (x - kLitBase));
+                        else if (x >= outS) v[r] = lds_u8(x);
+                        else v[r] = (uint32_t)__ldcg(dstB + (os - (int)(outS - x)));
+                    }
+                }
+                #pragma unroll
+                for (int r = 0; r < kRowsRpt; r++)
+                    if (p0 + (uint32_t)(r * kRowsThreads) < lim) sts_u8(outS + p0 + (uint32_t)(r * kRowsThreads), v[r]);
+                if (wv == nWaves - 1) fence_proxy_async();
+                __syncthreads();
+            }
+#else
             resolve(0);
             for (int wv = 0; wv < nWaves; wv++) {
                 if (wv > 0) { mbar_wait(&S.wbar, wpar); wpar ^= 1; }   /* every warp has copied wave wv-1 */
@@ -1015,6 +1039,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) lz4_expand_tiles_kernel(lz4k_
             }
             mbar_wait(&S.wbar, wpar);
             wpar ^= 1;
+#endif
         }
         /* ---- store: smem -> HBM ---- */
         {
