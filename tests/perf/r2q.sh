@@ -19,6 +19,5 @@ except Exception as e: print(f,'FAILED',e); print(open(f+'.err').read()[-2500:])
 PY
 }
 run peer_c4 --exchange peer --chunks 4
-run peer_c8 --exchange peer --chunks 8
-run peer_c2 --exchange peer --chunks 2
 run peer_c1 --exchange peer --chunks 1
+cp $O/r2q_n${N}_peer_c4.json $O/bench_r02_n$N.json
