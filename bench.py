@@ -45,11 +45,13 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--chunks", type=int, default=4, help="N > 1: pieces of a rank's shard whose exchange overlaps the decode of the next piece")
+    ap.add_argument("--chunks", type=int, default=1, help="N > 1: pieces of a rank's shard whose exchange overlaps the decode of the next piece")
     ap.add_argument("--ceiling", action="store_true",
                     help="also time the rows kernel's skeleton without the decode (TMA in/out only; + one LDS/STS per output byte)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: 'peer' = copy-engine pushes into the peers' frames (CUDA IPC over NVLink), 'nccl' = grouped NCCL send/recv")
+    ap.add_argument("--exchange", default="nccl", choices=["peer", "nccl"],
+                    help="N > 1: 'nccl' = grouped NCCL send/recv per chunk, 'peer' = copy-engine pushes into the peers' frames (CUDA IPC)")
+    ap.add_argument("--reserve-sms", type=int, default=0,
+                    help="N > 1: SMs the persistent decode kernels leave to the concurrent exchange kernels (LZ4B200_RESERVE_SMS)")
     return ap.parse_args()
 
 
@@ -585,7 +587,7 @@ def run_ours(args):
                if exchange == "peer" else "grouped NCCL send/recv per chunk")
         line["multi_gpu"] = {"value_includes": "decode + exchange of the decoded shards (%s; %d chunks, exchange of chunk k "
                                                "overlaps the decode of chunk k+1)" % (how, args.chunks),
-                             "exchange": exchange,
+                             "exchange": exchange, "chunks": args.chunks, "reserve_sms": args.reserve_sms,
                              "per_rank_ms_per_step": per_rank_ms,
                              "codec_only": {"ms_per_step_max_over_ranks": round(codec_ms_max, 4),
                                             "GBps": round(world * total / (codec_ms_max * 1e-3) / GB, 3)},
@@ -604,6 +606,8 @@ def run_ours(args):
 def main():
     global BLOCK, METRIC
     args = parse_args()
+    if args.reserve_sms > 0:
+        os.environ["LZ4B200_RESERVE_SMS"] = str(args.reserve_sms)          # read once by the library's first decode launch
     if args.block_kb != 64:
         BLOCK = args.block_kb * 1024
         METRIC = METRIC.replace("64 KB", "%d KB" % args.block_kb)

@@ -1487,7 +1487,11 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         if (e != cudaSuccess) return (int)e;
         const char* env = getenv("LZ4K_SCAN_IMPL");               /* developer A/B switch: "thread" | "par" | "split" */
         scanImpl = env ? (env[0] == 'p' ? 1 : env[0] == 's' ? 2 : 0) : -1;
-        sms = v;
+        /* LZ4B200_RESERVE_SMS = k: the persistent expand kernels leave k SMs alone, for a communication kernel that runs
+         * concurrently (N > 1: NCCL's send/recv of the previous chunk; bench.py --reserve-sms) */
+        const char* rs = getenv("LZ4B200_RESERVE_SMS");
+        const int reserve = rs ? atoi(rs) : 0;
+        sms = (reserve > 0 && reserve < v) ? v - reserve : v;
     }
     if (phases & 1) {
         cudaError_t e = cudaMemsetAsync(a->workspace, 0, 256, s);     // WsHeader: list counter

@@ -18,6 +18,7 @@ try:
 except Exception as e: print(f,'FAILED',e); print(open(f+'.err').read()[-2500:])
 PY
 }
-run peer_c4 --exchange peer --chunks 4
-run peer_c1 --exchange peer --chunks 1
-cp $O/r2q_n${N}_peer_c4.json $O/bench_r02_n$N.json
+run nccl_c4_r16 --exchange nccl --chunks 4 --reserve-sms 16
+run nccl_c4_r32 --exchange nccl --chunks 4 --reserve-sms 32
+run nccl_c8_r24 --exchange nccl --chunks 8 --reserve-sms 24
+run nccl_c1 --exchange nccl --chunks 1
