@@ -54,13 +54,14 @@ def chunk_ranges(n_units, n_chunks):
 
 
 class PeerFrame:
-    """Every rank's copy of the frame, mapped into every other rank's address space (CUDA IPC; NVLink peer memory).
+    """Every rank's copy of the frame, mapped into every other rank's address space (CUDA IPC).
 
     With it the exchange of a decoded chunk is R-1 device-to-device copies issued by the rank that decoded it, straight
-    into the chunk's final place in each peer's frame (LZ4B200_peer_copy_async).  The copies run on the GPU's copy engines, one stream per peer:
-    they take no SM away from the codec's persistent kernels -- NCCL's send/recv kernels do, which made the overlapped
-    NCCL exchange SLOWER than the serial one (2 GPUs, 4 GiB per rank: 19.5 ms with 4 chunks, 16.5 ms with one;
-    profiles/experiments_r02.txt).  Collective construction: every rank of `group` must call it with its own `full`."""
+    into the chunk's final place in each peer's frame (LZ4B200_peer_copy_async), on one stream per peer: copy engines, no
+    SM taken from the codec's persistent kernels.  MEASURED (2 B200s of an NVSwitch node, 4 GiB per rank): 27 GB/s -- the
+    copies into IPC-mapped memory do not take NVLink there -- against 650 GB/s for NCCL's send/recv kernels, so NCCL is the
+    default exchange and this class is for systems where peer copies are fast (profiles/experiments_r02.txt).
+    Collective construction: every rank of `group` must call it with its own `full`."""
 
     def __init__(self, full, group=None):
         from torch.multiprocessing.reductions import reduce_tensor
