@@ -213,7 +213,7 @@ def workload_config(n_blocks, gib, proba, accel, ratio, gpus):
             "l2": "the inputs of a step (%.1f GiB compressed + %.1f GiB decoded) exceed the 126 MB L2 and every CPU cache; no flush needed"
                   % (n_blocks * BLOCK / ratio / (1 << 30), n_blocks * BLOCK / (1 << 30)),
             "parallelism": "blocks partitioned contiguously over %d rank(s); for N > 1 the timed step ends with the exchange "
-                           "of the decoded shards (every rank holds the whole frame), overlapped chunk by chunk with the decode"
+                           "of the decoded shards (every rank holds the whole frame; --chunks > 1 overlaps it piecewise with the decode)"
                            % gpus}
 
 

@@ -1191,6 +1191,7 @@ __device__ int encode_block(const uint8_t* __restrict__ src, const int n, uint8_
                 const bool term = pnext > mflimit1;           // lz4.c:1055 fires at this visit
                 uint32_t v32 = 0, h = 0x80000000u | lane, old = 0;
                 if (!term) { h = T.hashv(src + p, v32); old = T.get(h); }
+                __syncwarp();                                 // every lane has read the table before any lane writes it (below)
                 const unsigned peers = __match_any_sync(kFull, h);
                 const unsigned lower = peers & ((1u << lane) - 1u);
                 const int fromLane = lower ? (31 - __clz(lower)) : lane;
