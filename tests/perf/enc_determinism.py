@@ -1,5 +1,10 @@
-"""Developer check: the parallel compressor must give the same bytes whatever the destination layout / capacity.
-Runs the same 8 blocks into differently laid out slot buffers and reports sizes, first differing byte, oracle decode."""
+"""Developer check: the parallel compressor must give the same, valid bytes whatever the destination layout / capacity --
+and whatever tool watches it.  Runs the same 8 blocks into differently laid out slot buffers and reports sizes, first
+differing byte and the oracle's decode of every block; `--poison` also fills the CTAs' shared memory with patterns before
+each run (a kernel that read shared memory it never wrote would give pattern-dependent output).
+Usage (under gpurun):  python tests/perf/enc_determinism.py [--poison]
+                       compute-sanitizer --tool memcheck python tests/perf/enc_determinism.py     (same sizes, every block decodes)
+This is the check that exposed the warp-cooperative match finish of round 2."""
 import os
 import sys
 
@@ -72,7 +77,8 @@ for cap in (int(ref_s.max()), int(ref_s.max()) - 1, int(ref_s.min()), int(ref_s.
         elif s[i] != 0:
             rep.append((i, "should not fit", int(s[i])))
     print("cap %d: %s" % (cap, "ok" if not rep else "BAD (block, size0, size, first diff, #diff, decodes) %s" % rep))
-sys.exit(0)
+if "--poison" not in sys.argv:
+    sys.exit(0)
 # ---- does the result depend on shared memory the kernel never wrote?  poison regions of it before a run ----
 import ctypes as C  # noqa: E402
 from lz4_b200 import _lib  # noqa: E402

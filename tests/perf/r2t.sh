@@ -1,9 +1,8 @@
 #!/bin/bash
-# bisect the parallel compressor's sanitizer-only corruption over its history (current tree, historical lz4_encode_par.cuh)
+# round 2, GPU calls T: the parallel compressor under the sanitizers (tests/perf/enc_determinism.py): plain, memcheck, racecheck
 set -u
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
-for c in branchfree nocoop mailbox; do
-  echo "== encoder of $c under memcheck"
-  LZ4_B200_LIBRARY=$PWD/lz4_b200/build/liblz4_b200_bis_$c.so TAG=bis timeout 400 compute-sanitizer --tool memcheck python tests/perf/enc_determinism.py 2>&1 | grep -E "run 0 sizes|DOES NOT|DIFFERS|ERROR SUMMARY|Error" | head -8 | cut -c1-300
-done
+echo "== plain"; TAG=plain timeout 300 python tests/perf/enc_determinism.py --poison 2>&1 | cut -c1-300
+echo "== memcheck"; TAG=memcheck timeout 600 compute-sanitizer --tool memcheck python tests/perf/enc_determinism.py 2>&1 | grep -v "^=========$" | cut -c1-300
+echo "== racecheck"; TAG=racecheck timeout 900 compute-sanitizer --tool racecheck python tests/perf/enc_determinism.py 2>&1 | grep -v "^=========$" | cut -c1-300
