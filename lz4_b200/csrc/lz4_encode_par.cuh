@@ -46,7 +46,6 @@ constexpr int kEpWin = kEpThreads * kEpPer;          /* 8192 positions per windo
 constexpr int kEpHashLog = 13;
 constexpr int kEpMaxSel = kEpPer / 4;                /* matches are >= 4 long: at most 4 selections per lane */
 constexpr int kEpSolo = 32;                          /* bytes a lane compares alone (> kEpPer: a longer match ends the lane's walk) */
-constexpr int kEpCoopRounds = 2;                     /* LZ4K_COOP2: long matches per warp-walk that the warp helps with */
 constexpr int kEpStage = kEpWin + 512;               /* a window's output is assembled here when it fits (it does unless literals of earlier windows come with it) */
 
 struct EncParSmem {
@@ -238,9 +237,6 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
              * is the lane's LAST selection (it covers the rest of the lane's 16 positions); its length is remembered, because the
              * lane may walk again from another entry and meet it again. */
             auto walk = [&](bool go, int e) {
-#ifdef LZ4K_COOP2
-                int pendK = -1;
-#endif
                 if (go) {
                     nSel = 0;
                     int rel = max(e - p0, 0);
@@ -256,14 +252,10 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                                 const int limit = matchlimit - p;
                                 c = ep_candidate_of_kind(S, src, head, p, c0, (uint32_t)(kinds >> (4 * rel)) & 15u);
                                 L = ep_extend(src, head, p, c, min(limit, kEpSolo));
-#ifdef LZ4K_COOP2
-                                if (L >= kEpSolo && L < limit) pendK = k;        /* a long match: the warp helps below */
-#else
                                 if (L >= kEpSolo && L < limit) {                 /* a long match: on, alone (see ep_extend_from), and remembered */
                                     L = ep_extend_from(src, head, p, c, L, limit);
                                     cacheP = p; cacheC = c; cacheL = L;
                                 }
-#endif
                             }
                             sPos[k] = p; sCand[k] = c; sLen[k] = L; sLit[k] = e;
                             nSel = k + 1;
@@ -273,53 +265,6 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                     }
                     exitE = e;
                 }
-#ifdef LZ4K_COOP2
-                /* Long matches, finished with the warp's help -- in STRAIGHT-LINE code: no branch around the loads, no loop whose
-                 * trip count depends on a vote (the form that compute-sanitizer's instrumentation breaks).  Up to
-                 * kEpCoopRounds pending lanes per walk get 512 bytes compared by the 32 lanes (4 x 128, first mismatch by a
-                 * shuffle minimum); what is left -- longer matches, further pending lanes -- is finished by its lane alone. */
-                unsigned pend = __ballot_sync(kFull, pendK >= 0);
-                #pragma unroll
-                for (int r = 0; r < kEpCoopRounds; r++) {
-                    const bool live = pend != 0u;
-                    const int sl = live ? __ffs(pend) - 1 : 0;
-                    pend &= pend - 1u;
-                    int jp = 0; uint32_t jc = 0;
-                    #pragma unroll
-                    for (int k = 0; k < kEpMaxSel; k++) if (k == pendK) { jp = sPos[k]; jc = sCand[k]; }
-                    jp = __shfl_sync(kFull, jp, sl); jc = __shfl_sync(kFull, jc, sl);
-                    const int limit = live ? matchlimit - jp : 0;            /* (no pending lane: every lane "stops" at once) */
-                    int best = 0x7FFFFFFF;
-                    #pragma unroll
-                    for (int it = 0; it < 4; it++) {
-                        const int o = kEpSolo + 128 * it + 4 * lane;
-                        const bool stop = o >= limit;
-                        const uint32_t oc = stop ? 0u : (uint32_t)o;            /* a stopped lane compares the match's first word with itself */
-                        const uint32_t x = ep_ld32(src, (uint32_t)(head + jp) + oc) ^ ep_ld32(src, (uint32_t)head + jc + oc);
-                        const int cand = stop ? o : (x ? o + ((__ffs(x) - 1) >> 3) : 0x7FFFFFFF);
-                        best = min(best, cand);
-                    }
-                    #pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(kFull, best, d));
-                    if (live && lane == sl) {
-                        int L = min(best == 0x7FFFFFFF ? kEpSolo + 512 : best, limit);
-                        if (best == 0x7FFFFFFF && L < limit) L = ep_extend_from(src, head, jp, jc, L, limit);
-                        #pragma unroll
-                        for (int k = 0; k < kEpMaxSel; k++) if (k == pendK) { sLen[k] = L; cacheP = sPos[k]; cacheC = sCand[k]; cacheL = L; }
-                        exitE = jp + L;
-                        pendK = -1;
-                    }
-                }
-                if (pendK >= 0) {                                              /* more pending lanes than rounds: alone */
-                    #pragma unroll
-                    for (int k = 0; k < kEpMaxSel; k++)
-                        if (k == pendK) {
-                            const int L = ep_extend_from(src, head, sPos[k], sCand[k], kEpSolo, matchlimit - sPos[k]);
-                            sLen[k] = L; cacheP = sPos[k]; cacheC = sCand[k]; cacheL = L;
-                            exitE = sPos[k] + L;
-                        }
-                }
-#endif
             };
             walk(true, eCur);
 #ifdef LZ4K_PHASE_TIMING
