@@ -26,7 +26,7 @@
  *           once: every lane walks its 16 positions as if the chain entered at its first position, a CTA-wide
  *           "last valid value" scan hands every lane the end of the last match selected before it, lanes whose
  *           search would start elsewhere walk again, until nothing changes.  Only SELECTED positions extend their
- *           match (4 bytes per step for the first 32, then 8), so the total comparison work is O(block size).
+ *           match (4 bytes per step, by the lane alone), so the total comparison work is O(block size).
  *   emit    backward extension (lz4.c:1107-1109), sizes, CTA-wide exclusive sum; every lane writes the headers of its
  *           sequences, the literals are copied position-parallel (every lane stores those of its 16 positions that are
  *           literals); a window's output is assembled in shared memory and written out in aligned 16-byte pieces
@@ -45,7 +45,7 @@ constexpr int kEpPer = 16;                           /* positions per thread and
 constexpr int kEpWin = kEpThreads * kEpPer;          /* 8192 positions per window */
 constexpr int kEpHashLog = 13;
 constexpr int kEpMaxSel = kEpPer / 4;                /* matches are >= 4 long: at most 4 selections per lane */
-constexpr int kEpSolo = 32;                          /* bytes a lane compares alone (> kEpPer: a longer match ends the lane's walk) */
+constexpr int kEpSolo = 32;                          /* a match at least this long (> kEpPer: it ends its lane's walk) is remembered across walks */
 constexpr int kEpStage = kEpWin + 512;               /* a window's output is assembled here when it fits (it does unless literals of earlier windows come with it) */
 
 struct EncParSmem {
@@ -117,7 +117,12 @@ __device__ __forceinline__ uint32_t ep_candidate_of_kind(const EncParSmem& S, co
     return kind == kEpKindWin ? (uint32_t)(c0 + 0xFFFF) - (tt >> 16) : (tt & 0xFFFFu) - 1u;
 }
 
-/* length of the match (p, c), both block positions, at most `limit` (>= 4): two word streams, 4 bytes per step */
+/* length of the match (p, c), both block positions, at most `limit` (>= 4): two word streams, 4 bytes per step.
+ * A lane extends its match ALONE, however long.  Round 2 also measured a warp-cooperative finish of matches >= 32 bytes
+ * (128 bytes per step through ballots: +12 % on P50, +20 % on P90) -- correct on the hardware, but under compute-sanitizer
+ * the instrumented loads inside its loop split the warp while the compiler, having proved the warp converged, emits bare
+ * VOTE / SHFL and a loop counter in a uniform register: the ballots see partial warps and matches come out too long.
+ * A kernel that the sanitizer cannot check is not worth 12 %; profiles/sanitizer_r02.txt, DESIGN.md 5.1. */
 __device__ __forceinline__ int ep_extend(const uint8_t* src, int head, int p, uint32_t c, int limit)
 {
     const uint32_t pa = (uint32_t)(head + p) + 4u, ca = (uint32_t)head + c + 4u;
@@ -133,26 +138,6 @@ __device__ __forceinline__ int ep_extend(const uint8_t* src, int head, int p, ui
         a0 = a1; b0 = b1; wa++; wb++; L += 4;
     }
     return L > limit ? limit : L;
-}
-
-/* The same from a known common length L0 (a multiple of 4 is not required) up to `limit`: 8 bytes per step.
- * A lane finishes a long match ALONE.  Round 2 also measured a warp-cooperative finish (128 bytes per step through ballots:
- * +12 % on P50, +20 % on P90) -- correct on the hardware, but under compute-sanitizer the instrumented loads inside its loop
- * split the warp while the compiler, having proved the warp converged, emits bare VOTE / SHFL and a loop counter in a
- * uniform register: the ballots then see partial warps and matches come out too long.  A kernel that cannot be checked
- * by the sanitizer is not worth 12 %; profiles/sanitizer_r02.txt, DESIGN.md 5.1. */
-__device__ __forceinline__ int ep_extend_from(const uint8_t* src, int head, int p, uint32_t c, int L0, int limit)
-{
-    int L = L0;
-    while (L + 8 <= limit) {
-        const uint32_t x0 = ep_ld32(src, (uint32_t)(head + p + L)) ^ ep_ld32(src, (uint32_t)head + c + (uint32_t)L);
-        const uint32_t x1 = ep_ld32(src, (uint32_t)(head + p + L + 4)) ^ ep_ld32(src, (uint32_t)head + c + (uint32_t)L + 4u);
-        if (x0) return L + ((__ffs(x0) - 1) >> 3);
-        if (x1) return L + 4 + ((__ffs(x1) - 1) >> 3);
-        L += 8;
-    }
-    while (L < limit && src[head + p + L] == src[(uint32_t)head + c + (uint32_t)L]) L++;
-    return L;
 }
 
 __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_encode_args a)
@@ -234,7 +219,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
             int cacheP = -1, cacheL = 0;                               /* the last long match this lane extended (walks repeat) */
             uint32_t cacheC = 0;
             /* One walk of every lane that `go`es: the lane's positions from the chain position e.  A match of kEpSolo bytes or more
-             * is the lane's LAST selection (it covers the rest of the lane's 16 positions); its length is remembered, because the
+             * covers the rest of the lane's 16 positions (it is the lane's LAST selection); its length is remembered, because the
              * lane may walk again from another entry and meet it again. */
             auto walk = [&](bool go, int e) {
                 if (go) {
@@ -251,11 +236,8 @@ __global__ void __launch_bounds__(kEpThreads, 2) lz4_encode_par_kernel(lz4k_enco
                             else {
                                 const int limit = matchlimit - p;
                                 c = ep_candidate_of_kind(S, src, head, p, c0, (uint32_t)(kinds >> (4 * rel)) & 15u);
-                                L = ep_extend(src, head, p, c, min(limit, kEpSolo));
-                                if (L >= kEpSolo && L < limit) {                 /* a long match: on, alone (see ep_extend_from), and remembered */
-                                    L = ep_extend_from(src, head, p, c, L, limit);
-                                    cacheP = p; cacheC = c; cacheL = L;
-                                }
+                                L = ep_extend(src, head, p, c, limit);           /* alone, whatever the length: see ep_extend */
+                                if (L >= kEpSolo) { cacheP = p; cacheC = c; cacheL = L; }      /* a long one is remembered */
                             }
                             sPos[k] = p; sCand[k] = c; sLen[k] = L; sLit[k] = e;
                             nSel = k + 1;
