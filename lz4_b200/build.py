@@ -46,7 +46,7 @@ def _run(cmd):
 
 def build(force=False, verbose=False, out=None, extra_defines=()):
     """Build the library.  `out` / `extra_defines` are for developer variants (experimental kernels built
-    next to the default library, e.g. out=build/liblz4_b200_pbv2.so, extra_defines=["LZ4K_PHASEB_V2"]);
+    next to the default library, e.g. out=build/liblz4_b200_barsync.so, extra_defines=["LZ4K_WAVE_BARSYNC"]);
     load one with LZ4_B200_LIBRARY=<path> (lz4_b200/_lib.py)."""
     lib = out or LIB
     if out is None and not extra_defines and not force and not _stale():
