@@ -127,7 +127,9 @@ LZ4B200_API int LZ4B200_decompress_blocks(const void* d_src, const int64_t* d_sr
  * The same call split in its two phases (phases: 1 = scan only -- validate every block and fill
  * d_outSize with the decoded sizes / error codes without moving data, the batched equivalent of
  * asking "what would LZ4_decompress_safe return"; 2 = expand only -- move the bytes of the
- * blocks a previous scan accepted, same arguments and workspace; 3 = both).
+ * blocks a previous scan accepted, same arguments and workspace; 3 = both).  An expand consumes what
+ * its scan left in the workspace (sizes, sequence marks, the list of blocks for the generic kernel): one
+ * expand per scan.
  */
 LZ4B200_API int LZ4B200_decompress_blocks_phased(const void* d_src, const int64_t* d_srcOff, const int32_t* d_srcSize,
                                                  void* d_dst, const int64_t* d_dstOff, int64_t dstStride,

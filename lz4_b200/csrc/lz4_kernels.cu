@@ -1528,6 +1528,11 @@ int lz4k_launch_decode(const lz4k_decode_args* a, int phases, void* stream)
         if (wide) {                                                  // blocks above 64 KB: one CTA per 60 KB output tile
             const int64_t units = a->nBlocks * (int64_t)tiles_of(a->dstCap);
             const int64_t grid = units < sms ? units : sms;          // all CTAs resident: a tile may wait for its predecessor
+            {   /* the tiles' done flags start at 0 for THIS expand (the index kernel clears them too; an expand repeated after one scan must not see the last one's) */
+                const WsView wv = ws_view(a->workspace, a->nBlocks, mark_stride(a->dstCapArr, a->dstCap, true), tiles_of(a->dstCap));
+                cudaError_t e = cudaMemsetAsync(wv.tileFlag, 0, (size_t)a->nBlocks * (wv.tilesMax + 1) * sizeof(uint32_t), s);
+                if (e != cudaSuccess) return (int)e;
+            }
             lz4_expand_tiles_kernel<<<(unsigned)grid, kRowsThreads, sizeof(RowsSmem), s>>>(*a);
         } else {
             int64_t grid = a->nBlocks < sms ? a->nBlocks : sms;      // persistent: one CTA per SM
