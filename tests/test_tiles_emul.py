@@ -127,3 +127,48 @@ def test_tiles_emulator_hand_made_sequences(emul):
         er2, eo2 = orc.decompress(comp, er)               # exact capacity: the end-of-block rules may reject a hand-made block
         r, got, st = run(emul, comp, er)
         assert r == er2 and (r <= 0 or got == eo2) and st[3] == 0, (name, "exact capacity", r, er2, st)
+
+
+def test_tiles_emulator_random_sequence_structures(emul):
+    """Randomly structured big blocks: literal runs from 0 to 70 000 bytes, matches from 4 to 150 000 bytes at offsets from 1 to
+    65 535 (self-overlapping ones included), so that runs start, end and straddle tile edges in every way."""
+    orc = Oracle()
+    rng = np.random.default_rng(2026)
+
+    def ext(v, out):
+        if v >= 15:
+            r = v - 15
+            while r >= 255:
+                out.append(255)
+                r -= 255
+            out.append(r)
+
+    for case in range(150):
+        out = bytearray()
+        produced = 0
+        target = int(rng.integers(70_000, 500_000))
+        while produced < target:
+            kind = rng.integers(0, 10)
+            ll = int(rng.choice([0, 1, 3, 14, 15, 16, 300, int(rng.integers(0, 70_000))], p=[.2, .15, .15, .1, .1, .1, .1, .1])) if kind else int(rng.integers(60_000, 70_000))
+            if produced == 0 and ll == 0:
+                ll = 1
+            mlen = int(rng.choice([4, 5, 18, 19, 20, 270, int(rng.integers(4, 150_000))], p=[.25, .15, .1, .1, .1, .1, .2]))
+            off = int(rng.choice([1, 2, 3, 4, 7, 8, 255, 4096, 61439, 61440, 61441, 65535, int(rng.integers(1, 65536))]))
+            off = max(1, min(off, produced + ll))
+            out.append((min(ll, 15) << 4) | min(mlen - 4, 15))
+            ext(ll, out)
+            out += bytes(rng.integers(0, 256, ll, dtype=np.uint8))
+            out += bytes([off & 255, off >> 8])
+            ext(mlen - 4, out)
+            produced += ll + mlen
+        last = bytes(rng.integers(0, 256, int(rng.integers(5, 40)), dtype=np.uint8))
+        out.append(min(len(last), 15) << 4)
+        ext(len(last), out)
+        out += last
+        comp = bytes(out)
+        er, eo = orc.decompress(comp, 1 << 20)
+        assert er > 65536, (case, er)
+        for cap in (er + 100, er):
+            er2, eo2 = orc.decompress(comp, cap)
+            r, got, st = run(emul, comp, cap)
+            assert r == er2 and (r <= 0 or got == eo2) and st[3] == 0, (case, cap, r, er2, st)
