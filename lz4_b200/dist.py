@@ -114,7 +114,7 @@ class PeerFrame:
         dist.all_reduce(self.token, group=self.group)          # a rank contributes only after its own pushes (stream order)
 
 
-def decode_and_allgather(full, blocks_per_rank, block_size, decode_chunk, n_chunks=4, group=None, peer=None):
+def decode_and_allgather(full, blocks_per_rank, block_size, decode_chunk, n_chunks=1, group=None, peer=None):
     """Decode this rank's shard chunk by chunk and exchange every chunk as soon as it is decoded, so that the
     exchange of chunk k runs while chunk k+1 is being decoded (the ordered-writer role of lz4io.c:594-635, spread
     over the ranks: afterwards every rank holds the whole decoded frame).
@@ -126,6 +126,8 @@ def decode_and_allgather(full, blocks_per_rank, block_size, decode_chunk, n_chun
     straight into their final place in `full` -- no staging buffer and no re-ordering copy, which a chunk-wise
     ncclAllGather (contiguous output per call) would need.  The collective stream waits for the decode of chunk k
     through the event torch.distributed records at issue time; the codec stream carries on with chunk k+1.
+    n_chunks = 1 (default) is the serial form, decode then exchange: measured faster than any overlap today, because
+    every extra chunk costs a whole scan kernel, whose time does not shrink with the batch.
     With `peer` (a PeerFrame over `full`) the exchange of a chunk is R-1 copy-engine copies into the peers' frames
     instead (no SM use; see PeerFrame).
     Returns the list of outstanding works (already waited for: the current stream is ordered after them)."""
